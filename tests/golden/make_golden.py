@@ -1,0 +1,227 @@
+"""
+Generate the golden fixtures in this directory by EXECUTING THE REFERENCE
+(``/root/reference``, LenslessPiCam v1.0.8) in the build container.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference cannot travel to the GPU box, so its outputs are committed here
+together with this script.  ``matplotlib`` and ``rawpy`` are not installed in
+the image; they are only imported at module top level by the reference
+(recon.py:166-167, utils/io.py:93) and never called on this path, so empty stub
+modules are created in a temp dir.
+
+Fixtures (all float32 inputs, seeded):
+
+* ``small_even_rgb``   24x32x3  -> padded 48x64     ADMM {1,5,30}, GD/Nesterov/FISTA {1,5,30}
+* ``small_odd_rgb``    23x38x3  -> padded 45x75 (odd x odd)  same
+* ``small_gray``       20x27x1  -> padded 40x54
+* ``small_mixed``      14x32x3  -> padded 27x64 (odd x even)
+* ``bundled_ds16``     the reference's bundled tape PSF + thumbs-up measurement
+                       through ``load_data(downsample=16)`` -> 190x253x3, ADMM-5/FISTA-20 outputs
+* ``convolver``        RealFFTConvolve2D pad/crop/convolve/deconvolve on the
+                       reference test's shapes (PSF 5x47x29x3, data 2x5x47x29x3 (the reference test uses batch 12); test_convolver.py:11-59)
+* ``batch``            UnrolledADMM.forward(batch) == per-sample ADMM
+
+Each npz stores inputs and, per algorithm/iteration count, the reference's
+torch-fp32 output (``t32``: the parity target), its numpy-fp32 output (``n32``)
+and torch-fp64 (``t64``: truth for error envelopes).
+"""
+
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def _import_reference():
+    stub = tempfile.mkdtemp(prefix="lpc_stubs_")
+    for mod in ("matplotlib", "rawpy"):
+        os.makedirs(os.path.join(stub, mod), exist_ok=True)
+        open(os.path.join(stub, mod, "__init__.py"), "w").close()
+    for sub in ("pyplot", "cm"):
+        open(os.path.join(stub, "matplotlib", sub + ".py"), "w").close()
+    sys.path.insert(0, stub)
+    sys.path.insert(0, REF)
+    import lensless  # noqa
+
+    return lensless
+
+
+def synth(h, w, C, seed, D=1):
+    rng = np.random.default_rng(seed)
+    psf = rng.random((D, h, w, C)) ** 8
+    psf /= np.linalg.norm(psf.ravel())
+    data = rng.random((1, h, w, C))
+    # a smooth-ish blob so TV / non-negativity are both active
+    yy, xx = np.mgrid[0:h, 0:w]
+    blob = np.exp(-(((yy - h / 2) / (h / 4)) ** 2 + ((xx - w / 3) / (w / 5)) ** 2))
+    data = 0.3 * data + 0.7 * blob[None, :, :, None]
+    data /= data.max()
+    return psf.astype(np.float32), data.astype(np.float32)
+
+
+def run_ref(lensless, torch, name, psf, data, n_iters, backend, **kw):
+    cls = getattr(lensless, name)
+    if backend == "n32":
+        p, d, dt = psf.copy(), data.copy(), "float32"
+    elif backend == "t32":
+        p, d, dt = torch.from_numpy(psf.copy()), torch.from_numpy(data.copy()), "float32"
+    else:
+        p, d, dt = (
+            torch.from_numpy(psf.astype(np.float64)),
+            torch.from_numpy(data.astype(np.float64)),
+            "float64",
+        )
+    out = {}
+    for n in n_iters:
+        rec = cls(p, dtype=dt, **kw)
+        rec.set_data(d)
+        res = rec.apply(n_iter=n, disp_iter=None, plot=False)
+        res = res.numpy() if hasattr(res, "numpy") else np.asarray(res)
+        out[n] = np.array(res, copy=True)
+    return out
+
+
+ALGOS = {"admm": "ADMM", "gd": "GradientDescent", "nesterov": "NesterovGradientDescent", "fista": "FISTA"}
+
+
+def make_case(lensless, torch, fname, psf, data, iters):
+    store = {"psf": psf, "data": data}
+    for key, cls in ALGOS.items():
+        for backend in ("t32", "n32", "t64"):
+            if backend == "n32" and key == "fista":
+                continue  # numpy FISTA upcasts to float64 under NumPy 2 (gd.py:238-239)
+            res = run_ref(lensless, torch, cls, psf, data, iters[key], backend)
+            for n, arr in res.items():
+                store[f"{key}_{backend}_{n}"] = arr
+    np.savez_compressed(os.path.join(HERE, fname), **store)
+    print("wrote", fname, {k: v.shape for k, v in store.items() if k in ("psf", "data")})
+
+
+def main():
+    lensless = _import_reference()
+    import torch
+
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    from lensless.recon.rfft_convolve import RealFFTConvolve2D
+
+    it = {"admm": (1, 5, 30), "gd": (1, 5, 30), "nesterov": (1, 5, 30), "fista": (1, 5, 30)}
+    make_case(lensless, torch, "small_even_rgb.npz", *synth(24, 32, 3, 1), it)
+    make_case(lensless, torch, "small_odd_rgb.npz", *synth(23, 38, 3, 2), it)
+    make_case(lensless, torch, "small_gray.npz", *synth(20, 27, 1, 3), it)
+    make_case(lensless, torch, "small_mixed.npz", *synth(14, 32, 3, 4), it)
+
+    # ---- ADMM with non-default parameters and a warm start (padded-shape initial_est, SURVEY 8b viii)
+    psf, data = synth(24, 32, 3, 5)
+    rng = np.random.default_rng(55)
+    init = rng.random((1, 48, 64, 3)).astype(np.float32) * 0.1
+    store = {"psf": psf, "data": data, "init": init}
+    kw = dict(mu1=3e-6, mu2=2e-5, mu3=1e-4, tau=3e-4)
+    for backend in ("t32", "t64"):
+        store[f"admm_params_{backend}_10"] = run_ref(lensless, torch, "ADMM", psf, data, (10,), backend, **kw)[10]
+    for backend, conv in (("t32", np.float32), ("t64", np.float64)):
+        rec = lensless.ADMM(torch.from_numpy(psf.astype(conv)), initial_est=torch.from_numpy(init.astype(conv).copy()))
+        rec.set_data(torch.from_numpy(data.astype(conv)))
+        store[f"admm_init_{backend}_10"] = rec.apply(n_iter=10, disp_iter=None, plot=False).numpy().copy()
+    # continuation: apply(5) then apply(5, reset=False) == apply(10)
+    rec = lensless.ADMM(torch.from_numpy(psf))
+    rec.set_data(torch.from_numpy(data))
+    rec.apply(n_iter=5, disp_iter=None, plot=False)
+    store["admm_cont_t32_5p5"] = rec.apply(n_iter=5, disp_iter=None, plot=False, reset=False).numpy().copy()
+    # background subtraction (recon.py:553-555)
+    bg = (rng.random((1, 24, 32, 3)) * 0.2).astype(np.float32)
+    rec = lensless.ADMM(torch.from_numpy(psf))
+    rec.set_data(torch.from_numpy(data.copy()))
+    store["bg"] = bg
+    store["admm_bg_t32_5"] = rec.apply(n_iter=5, disp_iter=None, plot=False, background=torch.from_numpy(bg)).numpy().copy()
+    # FISTA / GD with non-default tk / lip_fact
+    rec = lensless.FISTA(torch.from_numpy(psf), tk=2.0, lip_fact=1.2)
+    rec.set_data(torch.from_numpy(data))
+    store["fista_params_t32_10"] = rec.apply(n_iter=10, disp_iter=None, plot=False).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "variants.npz"), **store)
+    print("wrote variants.npz")
+
+    # ---- 3-D (depth) gradient descent: D independent planes sharing alpha / x0 (SURVEY 8a note)
+    psf3, _ = synth(16, 20, 3, 6, D=4)
+    _, data3 = synth(16, 20, 3, 7)
+    store = {"psf": psf3, "data": data3}
+    for key in ("gd", "fista"):
+        store[f"{key}_t32_10"] = run_ref(lensless, torch, ALGOS[key], psf3, data3, (10,), "t32")[10]
+        store[f"{key}_t64_10"] = run_ref(lensless, torch, ALGOS[key], psf3, data3, (10,), "t64")[10]
+    np.savez_compressed(os.path.join(HERE, "depth_gd.npz"), **store)
+    print("wrote depth_gd.npz")
+
+    # ---- convolver on the reference test's shapes (test_convolver.py)
+    rng = np.random.default_rng(7)
+    psf = rng.random((5, 47, 29, 3)).astype(np.float32)
+    data = rng.random((2, 5, 47, 29, 3)).astype(np.float32)
+    data_d1 = rng.random((2, 1, 47, 29, 3)).astype(np.float32)
+    store = {"psf": psf, "data": data, "data_d1": data_d1}
+    for norm in ("ortho", "backward"):
+        conv = RealFFTConvolve2D(torch.from_numpy(psf), pad=True, norm=norm)
+        store[f"padded_shape"] = np.array(conv._padded_shape)
+        store[f"start"] = np.array(conv._start_idx)
+        store[f"conv_{norm}"] = conv.convolve(torch.from_numpy(data)).numpy()
+        store[f"deconv_{norm}"] = conv.deconvolve(torch.from_numpy(data)).numpy()
+        store[f"conv_d1_{norm}"] = conv.convolve(torch.from_numpy(data_d1)).numpy()
+        if norm == "ortho":
+            store["H_ortho"] = conv._H.numpy()
+    conv = RealFFTConvolve2D(torch.from_numpy(psf), pad=False, norm="backward")
+    padded = conv._pad(torch.from_numpy(data))
+    store["conv_nopad"] = conv.convolve(padded).numpy()
+    store["deconv_nopad"] = conv.deconvolve(padded).numpy()
+    np.savez_compressed(os.path.join(HERE, "convolver.npz"), **store)
+    print("wrote convolver.npz")
+
+    # ---- batch: UnrolledADMM.forward(batch) (the only batched implementation)
+    psf, _ = synth(24, 32, 3, 8)
+    batch = np.stack([synth(24, 32, 3, 100 + b)[1] for b in range(4)])  # [4,1,24,32,3]
+    store = {"psf": psf, "batch": batch}
+    with torch.no_grad():
+        un = lensless.UnrolledADMM(torch.from_numpy(psf), n_iter=10)
+        store["unrolled_admm_t32_10"] = un.forward(torch.from_numpy(batch)).numpy().copy()
+    per = []
+    for b in range(4):
+        rec = lensless.ADMM(torch.from_numpy(psf))
+        rec.set_data(torch.from_numpy(batch[b]))
+        per.append(rec.apply(n_iter=10, disp_iter=None, plot=False).numpy().copy())
+    store["admm_t32_10"] = np.stack(per)
+    np.savez_compressed(os.path.join(HERE, "batch.npz"), **store)
+    print("wrote batch.npz")
+
+    # ---- bundled data through the reference's own loader (config 1 inputs)
+    from lensless.utils.io import load_data
+
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        psf, data = load_data(
+            psf_fp="data/psf/tape_rgb.png",
+            data_fp="data/raw_data/thumbs_up_rgb.png",
+            downsample=16,
+            plot=False,
+            dtype="float32",
+            normalize=True,
+        )
+    finally:
+        os.chdir(cwd)
+    psf = np.asarray(psf, dtype=np.float32)
+    data = np.asarray(data, dtype=np.float32)
+    store = {"psf": psf, "data": data}
+    for backend in ("t32", "n32", "t64"):
+        store[f"admm_{backend}_5"] = run_ref(lensless, torch, "ADMM", psf, data, (5,), backend)[5]
+    for backend in ("t32", "t64"):
+        store[f"admm_{backend}_100"] = run_ref(lensless, torch, "ADMM", psf, data, (100,), backend)[100]
+        store[f"fista_{backend}_20"] = run_ref(lensless, torch, "FISTA", psf, data, (20,), backend)[20]
+    np.savez_compressed(os.path.join(HERE, "bundled_ds16.npz"), **store)
+    print("wrote bundled_ds16.npz", psf.shape, data.shape)
+
+
+if __name__ == "__main__":
+    main()
