@@ -1,0 +1,177 @@
+/*
+ * lpc.h -- C-ABI of the B200-native iterative deconvolution engine
+ *          (liblpc.so, built from lenslesspicam_b200/csrc/ for sm_100a).
+ *
+ * The reference (LCAV/LenslessPiCam v1.0.8) is 100 % Python and has no FFI of
+ * its own; the boundary it exposes for this path is the Python class surface
+ *   lensless.recon.rfft_convolve.RealFFTConvolve2D   (rfft_convolve.py:26-223)
+ *   lensless.recon.recon.ReconstructionAlgorithm     (recon.py:179-653)
+ *   lensless.ADMM                                    (admm.py:24-338)
+ *   lensless.GradientDescent / NesterovGradientDescent / FISTA (gd.py:62-241)
+ * the lenslesspicam_b200 Python package mirrors that surface and binds the entry points below
+ * with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns LPC_OK (0) or a negative LPC_E* code; no C++
+ *     exception crosses the boundary; lpc_last_error() gives the message.
+ *   - every pointer named dev_* is a DEVICE pointer valid on the plan's device;
+ *     host_* pointers are host memory (pinned recommended).  The library never
+ *     takes ownership of caller memory.
+ *   - every call enqueues on the caller's stream (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream) and returns WITHOUT synchronising,
+ *     except where stated.
+ *   - caller arrays are in the reference's channels-last layout
+ *     data [B, D, h, w, C], PSF [D, h, w, C] (recon.py:223-224), contiguous unless
+ *     explicit element strides are given; `dtype` selects float or double.
+ *   - a plan is not re-entrant: one host thread / stream at a time per plan.
+ */
+#ifndef LPC_H_
+#define LPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPC_VERSION 100
+
+/* error codes */
+#define LPC_OK 0
+#define LPC_EINVAL -1   /* bad argument / shape / enum                                   */
+#define LPC_ECUDA -2    /* CUDA runtime error (message in lpc_last_error)                */
+#define LPC_ECUFFT -3   /* cuFFT error                                                    */
+#define LPC_ESTATE -4   /* call order: PSF or data not set, wrong algorithm for the call  */
+#define LPC_ENOMEM -5   /* device allocation failed                                       */
+#define LPC_ENOTIMPL -6 /* combination the reference raises NotImplementedError for       */
+
+/* algorithms (reference class each one replaces) */
+#define LPC_ALGO_CONV 0     /* RealFFTConvolve2D only         rfft_convolve.py:26  */
+#define LPC_ALGO_ADMM 1     /* lensless.ADMM                  admm.py:24           */
+#define LPC_ALGO_GD 2       /* lensless.GradientDescent       gd.py:62             */
+#define LPC_ALGO_NESTEROV 3 /* NesterovGradientDescent        gd.py:143            */
+#define LPC_ALGO_FISTA 4    /* lensless.FISTA                 gd.py:191            */
+
+/* dtype (recon.py:264-290: only float32 / float64 exist in the reference) */
+#define LPC_F32 0
+#define LPC_F64 1
+
+/* FFT normalisation of H (rfft_convolve.py:27,121-123; only H carries `norm`) */
+#define LPC_NORM_BACKWARD 0
+#define LPC_NORM_ORTHO 1
+#define LPC_NORM_FORWARD 2
+
+/* lpc_get_state selectors (planar -> channels-last, padded shape [B,D,Hp,Wp,C] unless noted) */
+#define LPC_STATE_IMAGE_EST 0 /* ADMM: V (padded). GD family: x (unpadded [B,D,h,w,C]) */
+#define LPC_STATE_FORWARD 1   /* ADMM: H V (padded)                                     */
+#define LPC_STATE_XI 2        /* ADMM: xi' = xi - mu1 X  (half-updated dual)  */
+#define LPC_STATE_RHO 3       /* ADMM: rho' = rho - mu3 W                                */
+#define LPC_STATE_ETA0 4      /* ADMM: eta'[...,0]                                       */
+#define LPC_STATE_ETA1 5      /* ADMM: eta'[...,1]                                       */
+
+/* lpc_plan_create flags */
+#define LPC_FLAG_NONE 0
+#define LPC_FLAG_NO_GRAPH 1   /* never capture the iteration loop in a CUDA graph        */
+#define LPC_FLAG_LITERAL 2    /* debug: reference's literal 6-FFT ADMM order (bisecting) */
+
+typedef struct lpc_plan_s* lpc_plan_t;
+
+int lpc_version(void);
+const char* lpc_error_name(int code);
+/* message of the last failure on `plan` (or, with plan == NULL, of the last
+ * failed lpc_plan_create on this thread). Valid until the next call. */
+const char* lpc_last_error(lpc_plan_t plan);
+
+/* ---- geometry: integer work, bit-exact with rfft_convolve.py:111-117 -------- */
+/* smallest 5-smooth integer >= n  (scipy.fftpack.next_fast_len, rfft_convolve.py:16,112) */
+int lpc_next_fast_len(int n);
+/* padded = next_fast_len(2*dim-1); start = (padded-dim)//2 */
+int lpc_geometry(int h, int w, int* Hp, int* Wp, int* start_y, int* start_x);
+
+/* ---- plan life cycle ------------------------------------------------------- */
+/* Allocates planar solver state, cuFFT plans and constant tables on `device`
+ * for B images of PSF-shape [D,h,w,C].  Replaces the constructor chain
+ * ADMM.__init__ (admm.py:35-135) / GradientDescent.__init__ (gd.py:67-92) ->
+ * ReconstructionAlgorithm.__init__ (recon.py:203-329) -> RealFFTConvolve2D.__init__
+ * (rfft_convolve.py:27-77).  `norm` is the convolver's norm (ADMM: backward,
+ * GD family: ortho).  `pad` mirrors RealFFTConvolve2D.pad and is only
+ * meaningful for LPC_ALGO_CONV (ADMM always optimises the padded image, the GD
+ * family the unpadded one). */
+int lpc_plan_create(lpc_plan_t* out, int device, int algo, int dtype, int norm, int B, int D,
+                    int C, int h, int w, int flags);
+int lpc_plan_destroy(lpc_plan_t plan);
+
+/* RealFFTConvolve2D.set_psf (rfft_convolve.py:102-131): pad PSF, H = rfft2(.)*norm,
+ * plus the algorithm constants derived from H: ADMM R_divmat (admm.py:186-190),
+ * GD step alpha and initial estimate (gd.py:96-112).  dev_psf is [D,h,w,C]. */
+int lpc_set_psf(lpc_plan_t plan, const void* dev_psf, void* stream);
+
+/* ADMM hyper-parameters (admm.py:39-42); recomputes R_divmat / X_divmat. */
+int lpc_set_admm_params(lpc_plan_t plan, double mu1, double mu2, double mu3, double tau,
+                        void* stream);
+/* GD family: lip_fact (gd.py:67), Nesterov mu (gd.py:153, always 0.9 after reset --
+ * SURVEY 8b quirk v), FISTA initial tk (gd.py:200). */
+int lpc_set_gd_params(lpc_plan_t plan, double lip_fact, double nesterov_mu, double fista_tk,
+                      void* stream);
+
+/* ReconstructionAlgorithm.set_data (recon.py:352-381) + optional background
+ * subtraction and clamp (recon.py:553-555; dev_background may be NULL).
+ * dev_data is [B, Dd, h, w, C] with Dd in {1, D}; strides are ELEMENT strides
+ * for (B, D, h, w, C); pass strides == NULL for contiguous.  dev_echo (may be
+ * NULL) receives the background-subtracted data, contiguous [B,Dd,h,w,C]: the
+ * reference overwrites self._data with it (recon.py:554). */
+int lpc_set_data(lpc_plan_t plan, const void* dev_data, int Dd, const int64_t* strides,
+                 const void* dev_background, const int64_t* bg_strides, void* dev_echo,
+                 void* stream);
+/* same from HOST memory: stages through an internal device buffer (cudaMemcpyAsync) */
+int lpc_set_data_host(lpc_plan_t plan, const void* host_data, int Dd, void* stream);
+
+/* reset() (admm.py:150-230, gd.py:94-126, 174-181, 227-233).  dev_initial_est is
+ * NULL or the warm start: ADMM [B,D,Hp,Wp,C] (padded! recon.py:296-299),
+ * GD family [B,D,h,w,C]. */
+int lpc_reset(lpc_plan_t plan, const void* dev_initial_est, void* stream);
+
+/* n_iter calls of _update (recon.py:575-576; admm.py:313-329; gd.py:132-134,
+ * 183-188, 235-241). Captured once per (plan, n_iter) into a CUDA graph unless
+ * LPC_FLAG_NO_GRAPH. */
+int lpc_run(lpc_plan_t plan, int n_iter, void* stream);
+
+/* _form_image (admm.py:331-338: crop + clamp; gd.py:136-140: non_neg) written
+ * channels-last to dev_out [B,D,h,w,C] (contiguous). */
+int lpc_get_image(lpc_plan_t plan, void* dev_out, void* stream);
+/* same into HOST memory; does NOT synchronise (caller syncs the stream). */
+int lpc_get_image_host(lpc_plan_t plan, void* host_out, void* stream);
+
+/* debug / parity: copy one state array out, channels-last (see LPC_STATE_*) */
+int lpc_get_state(lpc_plan_t plan, int which, void* dev_out, void* stream);
+/* H as the reference stores it: complex [D,Hp,Wp/2+1,C] interleaved (re,im)  (rfft_convolve.py:121-124) */
+int lpc_get_H(lpc_plan_t plan, void* dev_out, void* stream);
+/* GD step sizes alpha[C] (gd.py:108-112) */
+int lpc_get_alpha(lpc_plan_t plan, void* dev_out, void* stream);
+
+/* ---- RealFFTConvolve2D.convolve / deconvolve (rfft_convolve.py:133-223) ------ */
+/* LPC_ALGO_CONV plans only.  pad != 0: dev_in/out are [B,Dd,h,w,C] / [B,D,h,w,C];
+ * pad == 0: both are padded [B,*,Hp,Wp,C].  in_strides as in lpc_set_data
+ * (stride 0 broadcasts a size-1 depth or channel axis, test_convolver.py:32-59). */
+int lpc_convolve(lpc_plan_t plan, const void* dev_in, const int64_t* in_strides, void* dev_out,
+                 int adjoint, int pad, void* stream);
+
+/* ---- introspection for the roofline ------------------ */
+/* algorithmic bytes per iteration for the whole plan (all B images):
+ * ADMM 16P + 9.5Sp + d, GD family 10d + 6Sp. */
+int lpc_bytes_per_iter(lpc_plan_t plan, double* algorithmic_bytes);
+/* number of kernels (ours + cuFFT's) one iteration launches, ours only in *own */
+int lpc_launches_per_iter(lpc_plan_t plan, int* total, int* own);
+/* Runs n_iter iterations WITHOUT the CUDA graph, bracketing every phase of the
+ * iteration with CUDA events on `stream`; returns the mean device time (ms) of each
+ * phase in phase_ms[0..*n_phases) (at most 8).  Synchronises.  Names: lpc_phase_name. */
+int lpc_profile(lpc_plan_t plan, int n_iter, void* stream, double* phase_ms, int* n_phases);
+const char* lpc_phase_name(int algo, int phase);
+/* device bytes held by the plan */
+int lpc_plan_bytes(lpc_plan_t plan, size_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPC_H_ */

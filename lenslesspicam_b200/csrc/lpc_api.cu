@@ -1,0 +1,876 @@
+// lpc_api.cu -- C-ABI (include/lpc.h) over the sm_100a kernels and cuFFT.
+//
+// Host-side only: owns the planar solver state in HBM, the cuFFT plans and the CUDA
+// graph of the iteration loop.  No torch types, no exceptions across the boundary.
+#include "../../include/lpc.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lpc_admm.cuh"
+#include "lpc_gd.cuh"
+#include "lpc_setup.cuh"
+#include "lpc_util.cuh"
+
+using namespace lpc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int next_fast_len_impl(int n) {
+    // smallest 2^a 3^b 5^c >= n  (scipy.fftpack.next_fast_len; rfft_convolve.py:16,112)
+    if (n <= 6) return n < 0 ? 0 : n;
+    long long best = -1;
+    for (long long p5 = 1; p5 < 2LL * n; p5 *= 5) {
+        for (long long p35 = p5; p35 < 2LL * n; p35 *= 3) {
+            long long c = p35;
+            while (c < n) c *= 2;
+            if (best < 0 || c < best) best = c;
+        }
+    }
+    return (int)best;
+}
+
+template <typename T> struct FftTraits;
+template <> struct FftTraits<float> {
+    static constexpr cufftType R2C = CUFFT_R2C, C2R = CUFFT_C2R;
+    static cufftResult fwd(cufftHandle p, float* in, float2* out) { return cufftExecR2C(p, in, (cufftComplex*)out); }
+    static cufftResult inv(cufftHandle p, float2* in, float* out) { return cufftExecC2R(p, (cufftComplex*)in, out); }
+};
+template <> struct FftTraits<double> {
+    static constexpr cufftType R2C = CUFFT_D2Z, C2R = CUFFT_Z2D;
+    static cufftResult fwd(cufftHandle p, double* in, double2* out) { return cufftExecD2Z(p, in, (cufftDoubleComplex*)out); }
+    static cufftResult inv(cufftHandle p, double2* in, double* out) { return cufftExecZ2D(p, (cufftDoubleComplex*)in, out); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+struct lpc_plan_s {
+    int device = 0, algo = 0, dtype = 0, norm = 0, B = 1, D = 1, C = 1, h = 0, w = 0, flags = 0;
+    int Hp = 0, Wp = 0, sy = 0, sx = 0, Nh = 0, Np = 0, DC = 0;
+    std::string err;
+    virtual ~lpc_plan_s() {}
+    virtual int init() = 0;
+    virtual int set_psf(const void*, cudaStream_t) = 0;
+    virtual int set_admm_params(double, double, double, double, cudaStream_t) = 0;
+    virtual int set_gd_params(double, double, double, cudaStream_t) = 0;
+    virtual int set_data(const void*, int, const int64_t*, const void*, const int64_t*, void*, cudaStream_t) = 0;
+    virtual int set_data_host(const void*, int, cudaStream_t) = 0;
+    virtual int reset(const void*, cudaStream_t) = 0;
+    virtual int run(int, cudaStream_t) = 0;
+    virtual int get_image(void*, cudaStream_t) = 0;
+    virtual int get_image_host(void*, cudaStream_t) = 0;
+    virtual int get_state(int, void*, cudaStream_t) = 0;
+    virtual int get_H(void*, cudaStream_t) = 0;
+    virtual int get_alpha(void*, cudaStream_t) = 0;
+    virtual int convolve(const void*, const int64_t*, void*, int, int, cudaStream_t) = 0;
+    virtual int bytes_per_iter(double*) = 0;
+    virtual int launches_per_iter(int*, int*) = 0;
+    virtual int profile(int, cudaStream_t, double*, int*) = 0;
+    virtual size_t plan_bytes() = 0;
+};
+
+namespace {
+
+template <typename T>
+struct Plan : lpc_plan_s {
+    using Cplx = typename Cx<T>::type;
+    static constexpr int VEC = 16 / (int)sizeof(T);
+
+    // ---- sizes
+    int64_t plane = 0, splane = 0;
+    int dcol0 = 0, dpitch = 0, Dd = 1;
+    bool vec_ok = false;
+    // ---- device memory
+    std::vector<void*> allocs;
+    size_t total_bytes = 0;
+    T* psfpad = nullptr;   // [DC][Hp][Wp] zero-padded PSF (R2C input at set_psf)
+    Cplx* Hc = nullptr;    // [DC][Hp][Nh]  H = rfft2(pad(psf)) * norm
+    Cplx* Sy = nullptr;    // [Hp] ifftshift phase tables
+    Cplx* Sx = nullptr;    // [Nh]
+    T* consts = nullptr;   // [4C] hmax | psf min | psf max | alpha
+    T* data = nullptr;     // [B*Dd*C][h][dpitch] planar measurement
+    T* stage = nullptr;    // channels-last staging buffer for the *_host entry points
+    size_t stage_elems = 0;
+    // ADMM
+    T* VH = nullptr;       // [2][Np][plane]: V, HV   (C2R output)
+    T* AX = nullptr;       // [2][Np][plane]: a, xi'  (R2C input)
+    T* rho = nullptr;      // [Np][plane]    rho'
+    T* eta[2] = {nullptr, nullptr};  // ping-pong [2][Np][plane] eta'
+    T* Rn = nullptr;       // [DC][splane]  R_divmat / (Hp*Wp), real
+    Cplx* spec = nullptr;  // [nb][splane]
+    int eta_cur = 0;
+    // GD family / CONV
+    T* xpad = nullptr;     // [Np][plane] image estimate inside a zero border (R2C input)
+    T* dpad = nullptr;     // [Np][plane] residual inside a zero border (R2C input)
+    T* rpad = nullptr;     // [Np][plane] C2R output
+    T* mom = nullptr;      // [Np][h][w]  Nesterov p / FISTA xk_prev
+    bool xpad_border_dirty = false;
+    // ---- cuFFT
+    cufftHandle fwd_psf = 0, fwd = 0, inv = 0, fwd1 = 0, inv1 = 0;
+    bool have_fwd_psf = false, have_fwd = false, have_inv = false, have_1 = false;
+    void* work = nullptr;
+    size_t work_bytes = 0;
+    // ---- parameters / flags
+    double mu1 = 1e-6, mu2 = 1e-5, mu3 = 4e-5, tau = 1e-4;
+    double lip = 1.8, nmu = 0.9, tk0 = 1.0, tk = 1.0;
+    bool psf_set = false, data_set = false, state_ready = false, fista_first = true;
+    // ---- graph cache (one entry)
+    cudaGraphExec_t gexec = nullptr;
+    int g_niter = -1, g_eta = -1, g_first = -1;
+    double g_tk = 0;
+    cudaStream_t g_stream = nullptr;
+
+    ~Plan() override {
+        cudaSetDevice(device);
+        drop_graph();
+        if (have_fwd_psf) cufftDestroy(fwd_psf);
+        if (have_fwd) cufftDestroy(fwd);
+        if (have_inv) cufftDestroy(inv);
+        if (have_1) { cufftDestroy(fwd1); cufftDestroy(inv1); }
+        if (work) cudaFree(work);
+        for (void* p : allocs) cudaFree(p);
+    }
+
+    int fail(int code, const char* what, const char* detail) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "%s: %s (%s)", lpc_error_name(code), what, detail ? detail : "");
+        err = buf;
+        return code;
+    }
+#define LPC_CK(call)                                                                   \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) return fail(LPC_ECUDA, #call, cudaGetErrorString(e_));  \
+    } while (0)
+#define LPC_CF(call)                                                                   \
+    do {                                                                               \
+        cufftResult r_ = (call);                                                       \
+        if (r_ != CUFFT_SUCCESS) {                                                     \
+            char b_[32];                                                               \
+            snprintf(b_, sizeof b_, "cufftResult %d", (int)r_);                        \
+            return fail(LPC_ECUFFT, #call, b_);                                        \
+        }                                                                              \
+    } while (0)
+#define LPC_KCHECK() LPC_CK(cudaGetLastError())
+
+    template <typename U> int alloc(U** out, size_t n_elems) {
+        void* p = nullptr;
+        size_t bytes = n_elems * sizeof(U);
+        if (bytes == 0) bytes = sizeof(U);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(LPC_ENOMEM, "cudaMalloc", cudaGetErrorString(e)); }
+        e = cudaMemset(p, 0, bytes);
+        if (e != cudaSuccess) return fail(LPC_ECUDA, "cudaMemset", cudaGetErrorString(e));
+        allocs.push_back(p);
+        total_bytes += bytes;
+        *out = (U*)p;
+        return LPC_OK;
+    }
+
+    void drop_graph() {
+        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+        g_niter = -1;
+    }
+
+    int make_fft(cufftHandle* hnd, bool* have, cufftType type, int batch) {
+        LPC_CF(cufftCreate(hnd));
+        *have = true;
+        LPC_CF(cufftSetAutoAllocation(*hnd, 0));
+        int n[2] = {Hp, Wp};
+        size_t ws = 0;
+        LPC_CF(cufftMakePlanMany(*hnd, 2, n, nullptr, 1, 0, nullptr, 1, 0, type, batch, &ws));
+        if (ws > work_bytes) work_bytes = ws;
+        return LPC_OK;
+    }
+    int bind_work() {
+        if (work) { cudaFree(work); work = nullptr; }
+        if (work_bytes) {
+            cudaError_t e = cudaMalloc(&work, work_bytes);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(LPC_ENOMEM, "cudaMalloc(cufft work)", cudaGetErrorString(e)); }
+        }
+        if (have_fwd_psf) LPC_CF(cufftSetWorkArea(fwd_psf, work));
+        if (have_fwd) LPC_CF(cufftSetWorkArea(fwd, work));
+        if (have_inv) LPC_CF(cufftSetWorkArea(inv, work));
+        if (have_1) { LPC_CF(cufftSetWorkArea(fwd1, work)); LPC_CF(cufftSetWorkArea(inv1, work)); }
+        return LPC_OK;
+    }
+
+    int init() override {
+        LPC_CK(cudaSetDevice(device));
+        Hp = next_fast_len_impl(2 * h - 1);
+        Wp = next_fast_len_impl(2 * w - 1);
+        sy = (Hp - h) / 2;
+        sx = (Wp - w) / 2;
+        Nh = Wp / 2 + 1;
+        Np = B * D * C;
+        DC = D * C;
+        plane = (int64_t)Hp * Wp;
+        splane = (int64_t)Hp * Nh;
+        vec_ok = (Wp % VEC) == 0;
+        if (algo == LPC_ALGO_ADMM) {
+            dcol0 = sx - (sx % VEC);
+            dpitch = ((sx - dcol0) + w + VEC - 1) / VEC * VEC;
+        } else {
+            dcol0 = sx;
+            dpitch = w;
+        }
+        int rc;
+        if ((rc = alloc(&psfpad, (size_t)DC * plane))) return rc;
+        if ((rc = alloc(&Hc, (size_t)DC * splane))) return rc;
+        if ((rc = alloc(&Sy, (size_t)Hp))) return rc;
+        if ((rc = alloc(&Sx, (size_t)Nh))) return rc;
+        if ((rc = alloc(&consts, (size_t)4 * C))) return rc;
+        if ((rc = alloc(&data, (size_t)Np * h * dpitch))) return rc;  // sized for Dd == D
+        int nb = Np;
+        if (algo == LPC_ALGO_ADMM) {
+            nb = 2 * Np;
+            if ((rc = alloc(&VH, (size_t)2 * Np * plane))) return rc;
+            if ((rc = alloc(&AX, (size_t)2 * Np * plane))) return rc;
+            if ((rc = alloc(&rho, (size_t)Np * plane))) return rc;
+            if ((rc = alloc(&eta[0], (size_t)2 * Np * plane))) return rc;
+            if ((rc = alloc(&eta[1], (size_t)2 * Np * plane))) return rc;
+            if ((rc = alloc(&Rn, (size_t)DC * splane))) return rc;
+        } else {
+            if ((rc = alloc(&xpad, (size_t)Np * plane))) return rc;
+            if ((rc = alloc(&rpad, (size_t)Np * plane))) return rc;
+            if (algo != LPC_ALGO_CONV) {
+                if ((rc = alloc(&dpad, (size_t)Np * plane))) return rc;
+                if (algo != LPC_ALGO_GD)
+                    if ((rc = alloc(&mom, (size_t)Np * h * w))) return rc;
+            }
+        }
+        if ((rc = alloc(&spec, (size_t)nb * splane))) return rc;
+        if ((rc = make_fft(&fwd_psf, &have_fwd_psf, FftTraits<T>::R2C, DC))) return rc;
+        if ((rc = make_fft(&fwd, &have_fwd, FftTraits<T>::R2C, nb))) return rc;
+        if ((rc = make_fft(&inv, &have_inv, FftTraits<T>::C2R, nb))) return rc;
+        if ((rc = bind_work())) return rc;
+        // shift tables do not depend on the PSF
+        k_shift_table<T><<<(Hp + 127) / 128, 128>>>(Sy, Hp, Hp);
+        k_shift_table<T><<<(Nh + 127) / 128, 128>>>(Sx, Nh, Wp);
+        LPC_KCHECK();
+        LPC_CK(cudaDeviceSynchronize());
+        return LPC_OK;
+    }
+
+    // ---------------------------------------------------------------- layout helpers
+    static Strides5 contiguous(int Dn, int hh, int ww, int Cn) {
+        Strides5 s;
+        s.c = 1; s.x = Cn; s.y = (int64_t)ww * Cn; s.d = (int64_t)hh * ww * Cn; s.b = (int64_t)Dn * hh * ww * Cn;
+        return s;
+    }
+    static Strides5 from_array(const int64_t* a) { Strides5 s; s.b = a[0]; s.d = a[1]; s.y = a[2]; s.x = a[3]; s.c = a[4]; return s; }
+
+    int pack(const T* src, Strides5 ss, const T* bg, Strides5 bs, T* dst, int nB, int Dn, int hh, int ww,
+             int64_t plane_stride, int pitch, int oy, int ox, cudaStream_t st, T* echo = nullptr) {
+        dim3 grid((ww * C + 255) / 256, hh, nB * Dn);
+        k_pack<T><<<grid, 256, 0, st>>>(src, ss, bg, bs, dst, echo, Dn, C, hh, ww, plane_stride, pitch, oy, ox);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+    int unpack(const T* src, int64_t plane_stride, int pitch, int oy, int ox, T* dst, int nBD, int hh, int ww,
+               int clamp, cudaStream_t st) {
+        dim3 grid((ww * C + 255) / 256, hh, nBD);
+        k_unpack<T><<<grid, 256, 0, st>>>(src, plane_stride, pitch, oy, ox, dst, C, hh, ww, clamp);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+
+    AdmmK<T> admm_k() const {
+        AdmmK<T> k;
+        k.mu1 = (T)mu1; k.mu2 = (T)mu2; k.mu3 = (T)mu3;
+        k.thr = (T)(tau / mu2);
+        // X_divmat = 1/(pad(ones) + mu1) in the working precision (admm.py:193)
+        k.xdiv_in = T(1) / (T(1) + (T)mu1);
+        k.xdiv_out = T(1) / (T(0) + (T)mu1);
+        k.Hp = Hp; k.Wp = Wp; k.h = h; k.w = w; k.sy = sy; k.sx = sx;
+        k.C = C; k.D = D; k.Dd = Dd; k.dcol0 = dcol0; k.dpitch = dpitch;
+        k.plane = plane; k.dplane = (int64_t)h * dpitch; k.n_planes = Np;
+        return k;
+    }
+    GdK gd_k() const {
+        GdK k;
+        k.Hp = Hp; k.Wp = Wp; k.Nh = Nh; k.h = h; k.w = w; k.sy = sy; k.sx = sx;
+        k.C = C; k.D = D; k.Dd = Dd; k.dpitch = dpitch; k.plane = plane; k.dplane = (int64_t)h * dpitch;
+        k.n_planes = Np;
+        return k;
+    }
+
+    // ---------------------------------------------------------------- PSF
+    int compute_R(cudaStream_t st) {
+        k_admm_R<T><<<1184, 256, 0, st>>>(Hc, Rn, DC, Hp, Wp, Nh, mu1, mu2, mu3);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+    int compute_alpha(cudaStream_t st) {
+        k_alpha<T><<<1, 32, 0, st>>>(consts, C, (T)lip);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+
+    int set_psf(const void* dev_psf, cudaStream_t st) override {
+        LPC_CK(cudaSetDevice(device));
+        if (!dev_psf) return fail(LPC_EINVAL, "set_psf", "null PSF");
+        drop_graph();
+        const T* psf = (const T*)dev_psf;
+        int rc;
+        // pad (rfft_convolve.py:84-100) -> rfft2 (rfft_convolve.py:121-123)
+        if ((rc = pack(psf, contiguous(D, h, w, C), nullptr, Strides5{}, psfpad, 1, D, h, w, plane, Wp, sy, sx, st))) return rc;
+        LPC_CF(cufftSetStream(fwd_psf, st));
+        LPC_CF(FftTraits<T>::fwd(fwd_psf, psfpad, Hc));
+        if (norm != LPC_NORM_BACKWARD) {
+            const double n = (double)Hp * (double)Wp;
+            const T scale = (T)(norm == LPC_NORM_ORTHO ? 1.0 / std::sqrt(n) : 1.0 / n);
+            k_scale_complex<T><<<1184, 256, 0, st>>>(Hc, (int64_t)DC * splane, scale);
+            LPC_KCHECK();
+        }
+        // constants derived from H / PSF
+        k_init_consts<T><<<1, 32, 0, st>>>(consts, psf, C);
+        LPC_KCHECK();
+        {
+            dim3 g(64, DC);
+            k_hh_max<T><<<g, 256, 0, st>>>(Hc, consts, C, splane);
+            dim3 g2(64, C);
+            k_psf_minmax<T><<<g2, 256, 0, st>>>(psf, (int64_t)D * h * w, C, consts + C, consts + 2 * C);
+            LPC_KCHECK();
+        }
+        if ((rc = compute_alpha(st))) return rc;
+        if (algo == LPC_ALGO_ADMM && (rc = compute_R(st))) return rc;
+        psf_set = true;
+        state_ready = false;
+        return LPC_OK;
+    }
+
+    int set_admm_params(double a, double b, double c, double d, cudaStream_t st) override {
+        if (algo != LPC_ALGO_ADMM) return fail(LPC_ESTATE, "set_admm_params", "not an ADMM plan");
+        if (!(a > 0) || !(b > 0) || !(c > 0)) return fail(LPC_EINVAL, "set_admm_params", "mu must be > 0");
+        LPC_CK(cudaSetDevice(device));
+        mu1 = a; mu2 = b; mu3 = c; tau = d;
+        drop_graph();
+        if (psf_set) return compute_R(st);
+        return LPC_OK;
+    }
+    int set_gd_params(double lip_fact, double nesterov_mu, double fista_tk, cudaStream_t st) override {
+        if (algo < LPC_ALGO_GD) return fail(LPC_ESTATE, "set_gd_params", "not a gradient-descent plan");
+        LPC_CK(cudaSetDevice(device));
+        lip = lip_fact; nmu = nesterov_mu; tk0 = fista_tk;
+        drop_graph();
+        if (psf_set) return compute_alpha(st);
+        return LPC_OK;
+    }
+
+    // ---------------------------------------------------------------- data
+    int set_data(const void* dev_data, int Dd_in, const int64_t* strides, const void* dev_bg,
+                 const int64_t* bg_strides, void* dev_echo, cudaStream_t st) override {
+        if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "set_data", "convolver plans take their input in lpc_convolve");
+        if (!dev_data) return fail(LPC_EINVAL, "set_data", "null data");
+        if (Dd_in != 1 && Dd_in != D) return fail(LPC_EINVAL, "set_data", "data depth must be 1 or the PSF depth");
+        LPC_CK(cudaSetDevice(device));
+        if (Dd_in != Dd) drop_graph();
+        Dd = Dd_in;
+        Strides5 ss = strides ? from_array(strides) : contiguous(Dd, h, w, C);
+        Strides5 bs = bg_strides ? from_array(bg_strides) : contiguous(Dd, h, w, C);
+        // the data planes were zero-filled at allocation and only the true window is ever
+        // written, so the alignment slack of the ADMM layout stays zero
+        int rc = pack((const T*)dev_data, ss, (const T*)dev_bg, bs, data, B, Dd, h, w, (int64_t)h * dpitch, dpitch, 0,
+                      sx - dcol0, st, (T*)dev_echo);
+        if (rc) return rc;
+        data_set = true;
+        return LPC_OK;
+    }
+    int ensure_stage(size_t elems) {
+        if (elems <= stage_elems) return LPC_OK;
+        int rc = alloc(&stage, elems);  // the old one (if any) is released with the plan
+        if (rc) return rc;
+        stage_elems = elems;
+        return LPC_OK;
+    }
+    int set_data_host(const void* host, int Dd_in, cudaStream_t st) override {
+        if (!host) return fail(LPC_EINVAL, "set_data_host", "null data");
+        if (Dd_in != 1 && Dd_in != D) return fail(LPC_EINVAL, "set_data_host", "data depth must be 1 or the PSF depth");
+        LPC_CK(cudaSetDevice(device));
+        size_t n = (size_t)B * D * h * w * C;
+        int rc = ensure_stage(n);
+        if (rc) return rc;
+        LPC_CK(cudaMemcpyAsync(stage, host, (size_t)B * Dd_in * h * w * C * sizeof(T), cudaMemcpyHostToDevice, st));
+        return set_data(stage, Dd_in, nullptr, nullptr, nullptr, nullptr, st);
+    }
+
+    // ---------------------------------------------------------------- reset
+    int ensure_single_plans() {
+        if (have_1) return LPC_OK;
+        int rc;
+        bool h1 = false, h2 = false;
+        if ((rc = make_fft(&fwd1, &h1, FftTraits<T>::R2C, Np))) return rc;
+        if ((rc = make_fft(&inv1, &h2, FftTraits<T>::C2R, Np))) return rc;
+        have_1 = true;
+        LPC_CK(cudaDeviceSynchronize());  // the shared work area may be re-allocated
+        return bind_work();
+    }
+
+    int spec_mul(Cplx* s, int nplanes, int adjoint, cudaStream_t st) {
+        dim3 grid((unsigned)((splane + 255) / 256), nplanes);
+        const T scale = (T)(1.0 / ((double)Hp * (double)Wp));
+        k_spec_mul<T><<<grid, 256, 0, st>>>(s, Hc, Sy, Sx, DC, Hp, Nh, adjoint, scale);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+
+    int reset(const void* dev_init, cudaStream_t st) override {
+        if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "reset", "convolver plans have no solver state");
+        if (!psf_set) return fail(LPC_ESTATE, "reset", "PSF not set");
+        LPC_CK(cudaSetDevice(device));
+        int rc;
+        if (algo == LPC_ALGO_ADMM) {
+            // admm.py:150-183: every state array zero, or the warm start
+            LPC_CK(cudaMemsetAsync(VH, 0, (size_t)2 * Np * plane * sizeof(T), st));
+            LPC_CK(cudaMemsetAsync(AX, 0, (size_t)2 * Np * plane * sizeof(T), st));
+            LPC_CK(cudaMemsetAsync(rho, 0, (size_t)Np * plane * sizeof(T), st));
+            LPC_CK(cudaMemsetAsync(eta[0], 0, (size_t)2 * Np * plane * sizeof(T), st));
+            eta_cur = 0;
+            if (dev_init) {
+                if ((rc = ensure_single_plans())) return rc;
+                // V = initial_est (padded shape, recon.py:296-299)
+                if ((rc = pack((const T*)dev_init, contiguous(D, Hp, Wp, C), nullptr, Strides5{}, VH, B, D, Hp, Wp, plane,
+                               Wp, 0, 0, st))) return rc;
+                // HV = convolve(V) (admm.py:175)
+                LPC_CF(cufftSetStream(fwd1, st));
+                LPC_CF(cufftSetStream(inv1, st));
+                LPC_CF(FftTraits<T>::fwd(fwd1, VH, spec));
+                if ((rc = spec_mul(spec, Np, 0, st))) return rc;
+                LPC_CF(FftTraits<T>::inv(inv1, spec, VH + (int64_t)Np * plane));
+                dim3 grid((Wp + 127) / 128, Hp, Np);
+                k_admm_warm_start<T><<<grid, 128, 0, st>>>(admm_k(), VH, VH + (int64_t)Np * plane, AX + (int64_t)Np * plane,
+                                                          rho, eta[0]);
+                LPC_KCHECK();
+            }
+        } else {
+            // gd.py:94-126
+            if (dev_init) {
+                if ((rc = pack((const T*)dev_init, contiguous(D, h, w, C), nullptr, Strides5{}, xpad, B, D, h, w, plane, Wp,
+                               sy, sx, st))) return rc;
+            } else {
+                dim3 grid((w + 127) / 128, h, Np);
+                k_fill_x0<T><<<grid, 128, 0, st>>>(xpad, consts, C, h, w, plane, Wp, sy, sx);
+                LPC_KCHECK();
+            }
+            if (mom) LPC_CK(cudaMemsetAsync(mom, 0, (size_t)Np * h * w * sizeof(T), st));
+            tk = tk0;            // gd.py:227-233
+            fista_first = true;  // xk aliases x right after reset (gd.py:233)
+        }
+        state_ready = true;
+        return LPC_OK;
+    }
+
+    // ---------------------------------------------------------------- iterations
+    // ev (optional): n_phases+1 events recorded at the phase boundaries (lpc_profile)
+    int admm_iteration(cudaStream_t st, cudaEvent_t* ev = nullptr) {
+#define LPC_EV(i) do { if (ev) LPC_CK(cudaEventRecord(ev[i], st)); } while (0)
+        LPC_EV(0);
+        const AdmmK<T> k = admm_k();
+        T* a = AX;
+        T* xi = AX + (int64_t)Np * plane;
+        const T* V = VH;
+        const T* HV = VH + (int64_t)Np * plane;
+        if (vec_ok) {
+            constexpr int RY = 8;
+            const int nvec = Wp / VEC;
+            const int64_t nwarps = (int64_t)Np * ((Hp + RY - 1) / RY) * ((nvec + 31) / 32);
+            const unsigned blocks = (unsigned)((nwarps + 7) / 8);
+            k_admm_spatial_vec<T, RY><<<blocks, 256, 0, st>>>(k, V, HV, data, xi, rho, eta[eta_cur], eta[eta_cur ^ 1], a);
+        } else {
+            dim3 grid((Wp + 127) / 128, Hp, Np);
+            k_admm_spatial_generic<T><<<grid, 128, 0, st>>>(k, V, HV, data, xi, rho, eta[eta_cur], eta[eta_cur ^ 1], a);
+        }
+        LPC_KCHECK();
+        eta_cur ^= 1;
+        LPC_EV(1);
+        LPC_CF(FftTraits<T>::fwd(fwd, AX, spec));
+        LPC_EV(2);
+        dim3 grid((unsigned)((splane + 255) / 256), Np);
+        k_admm_spectral<T><<<grid, 256, 0, st>>>(spec, Hc, Rn, Sy, Sx, Np, DC, Hp, Nh);
+        LPC_KCHECK();
+        LPC_EV(3);
+        LPC_CF(FftTraits<T>::inv(inv, spec, VH));
+        LPC_EV(4);
+        return LPC_OK;
+    }
+
+    int gd_iteration(cudaStream_t st, cudaEvent_t* ev = nullptr) {
+        const GdK k = gd_k();
+        int rc;
+        LPC_EV(0);
+        // convolve(x): pad is implicit (x lives in xpad's window)
+        LPC_CF(FftTraits<T>::fwd(fwd, xpad, spec));
+        LPC_EV(1);
+        if ((rc = spec_mul(spec, Np, 0, st))) return rc;
+        LPC_EV(2);
+        LPC_CF(FftTraits<T>::inv(inv, spec, rpad));
+        LPC_EV(3);
+        dim3 grid((w + 127) / 128, h, Np);
+        k_gd_residual<T><<<grid, 128, 0, st>>>(k, rpad, data, dpad);
+        LPC_KCHECK();
+        LPC_EV(4);
+        // deconvolve(residual)
+        LPC_CF(FftTraits<T>::fwd(fwd, dpad, spec));
+        LPC_EV(5);
+        if ((rc = spec_mul(spec, Np, 1, st))) return rc;
+        LPC_EV(6);
+        LPC_CF(FftTraits<T>::inv(inv, spec, rpad));
+        LPC_EV(7);
+        if (algo == LPC_ALGO_GD) {
+            k_gd_update<T><<<grid, 128, 0, st>>>(k, rpad, consts, xpad);
+        } else if (algo == LPC_ALGO_NESTEROV) {
+            k_nesterov_update<T><<<grid, 128, 0, st>>>(k, rpad, consts, xpad, mom, (T)nmu);
+        } else {
+            // gd.py:238-240: t_{k+1} = (1 + sqrt(1 + 4 t_k^2))/2 ; beta = (t_k - 1)/t_{k+1}
+            const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
+            const T beta = (T)((tk - 1.0) / tn);
+            k_fista_update<T><<<grid, 128, 0, st>>>(k, rpad, consts, xpad, mom, beta, fista_first ? 1 : 0);
+            tk = tn;
+            fista_first = false;
+        }
+        LPC_KCHECK();
+        LPC_EV(8);
+        return LPC_OK;
+    }
+#undef LPC_EV
+
+    // per-phase device times of the un-graphed iteration, CUDA events on the launching stream
+    int profile(int n_iter, cudaStream_t st, double* ms, int* n_phases) override {
+        if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "profile", "convolver plans do not iterate");
+        if (!psf_set || !data_set || !state_ready) return fail(LPC_ESTATE, "profile", "PSF, data and reset first");
+        LPC_CK(cudaSetDevice(device));
+        LPC_CF(cufftSetStream(fwd, st));
+        LPC_CF(cufftSetStream(inv, st));
+        const int np = (algo == LPC_ALGO_ADMM) ? 4 : 8;
+        cudaEvent_t ev[9];
+        for (int i = 0; i <= np; ++i) LPC_CK(cudaEventCreate(&ev[i]));
+        for (int i = 0; i < np; ++i) ms[i] = 0.0;
+        int rc = LPC_OK;
+        for (int it = 0; it < n_iter && rc == LPC_OK; ++it) {
+            rc = (algo == LPC_ALGO_ADMM) ? admm_iteration(st, ev) : gd_iteration(st, ev);
+            if (rc != LPC_OK) break;
+            LPC_CK(cudaEventSynchronize(ev[np]));
+            for (int i = 0; i < np; ++i) {
+                float t = 0.f;
+                LPC_CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+                ms[i] += (double)t;
+            }
+        }
+        for (int i = 0; i <= np; ++i) cudaEventDestroy(ev[i]);
+        if (rc == LPC_OK && n_iter > 0) for (int i = 0; i < np; ++i) ms[i] /= n_iter;
+        *n_phases = np;
+        return rc;
+    }
+
+    int iterate(int n_iter, cudaStream_t st) {
+        int rc = LPC_OK;
+        for (int i = 0; i < n_iter && rc == LPC_OK; ++i) rc = (algo == LPC_ALGO_ADMM) ? admm_iteration(st) : gd_iteration(st);
+        return rc;
+    }
+
+    int run(int n_iter, cudaStream_t st) override {
+        if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "run", "convolver plans do not iterate");
+        if (!psf_set || !data_set) return fail(LPC_ESTATE, "run", "PSF and data must be set first");
+        if (!state_ready) return fail(LPC_ESTATE, "run", "call lpc_reset first");
+        if (n_iter < 0) return fail(LPC_EINVAL, "run", "n_iter < 0");
+        if (n_iter == 0) return LPC_OK;
+        LPC_CK(cudaSetDevice(device));
+        LPC_CF(cufftSetStream(fwd, st));
+        LPC_CF(cufftSetStream(inv, st));
+        static const bool env_no_graph = (getenv("LPC_NO_GRAPH") != nullptr);
+        const bool use_graph = !(flags & LPC_FLAG_NO_GRAPH) && !env_no_graph && st != nullptr;
+        if (!use_graph) return iterate(n_iter, st);
+
+        const int first = fista_first ? 1 : 0;
+        const bool hit = gexec && g_niter == n_iter && g_eta == eta_cur && g_stream == st &&
+                         (algo != LPC_ALGO_FISTA || (g_tk == tk && g_first == first));
+        if (!hit) {
+            drop_graph();
+            const int eta0 = eta_cur;
+            const double tk_start = tk;
+            cudaGraph_t graph = nullptr;
+            LPC_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = iterate(n_iter, st);
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc != LPC_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+            if (e != cudaSuccess) return fail(LPC_ECUDA, "cudaStreamEndCapture", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { gexec = nullptr; return fail(LPC_ECUDA, "cudaGraphInstantiate", cudaGetErrorString(e)); }
+            g_niter = n_iter; g_eta = eta0; g_tk = tk_start; g_first = first; g_stream = st;
+            // iterate() advanced the host-side bookkeeping while capturing; nothing ran yet
+        } else {
+            // replay: advance the host-side bookkeeping exactly as iterate() would
+            if (algo == LPC_ALGO_ADMM) eta_cur ^= (n_iter & 1);
+            if (algo == LPC_ALGO_FISTA) {
+                for (int i = 0; i < n_iter; ++i) tk = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
+                fista_first = false;
+            }
+        }
+        LPC_CK(cudaGraphLaunch(gexec, st));
+        return LPC_OK;
+    }
+
+    // ---------------------------------------------------------------- outputs
+    int get_image(void* dev_out, cudaStream_t st) override {
+        if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "get_image", "convolver plans have no image");
+        if (!state_ready) return fail(LPC_ESTATE, "get_image", "no state: call lpc_reset");
+        if (!dev_out) return fail(LPC_EINVAL, "get_image", "null output");
+        LPC_CK(cudaSetDevice(device));
+        const T* src = (algo == LPC_ALGO_ADMM) ? VH : xpad;
+        return unpack(src, plane, Wp, sy, sx, (T*)dev_out, B * D, h, w, 1, st);
+    }
+    int get_image_host(void* host_out, cudaStream_t st) override {
+        if (!host_out) return fail(LPC_EINVAL, "get_image_host", "null output");
+        size_t n = (size_t)B * D * h * w * C;
+        int rc = ensure_stage(n);
+        if (rc) return rc;
+        if ((rc = get_image(stage, st))) return rc;
+        LPC_CK(cudaMemcpyAsync(host_out, stage, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+        return LPC_OK;
+    }
+    int get_state(int which, void* dev_out, cudaStream_t st) override {
+        if (!state_ready) return fail(LPC_ESTATE, "get_state", "no state: call lpc_reset");
+        if (!dev_out) return fail(LPC_EINVAL, "get_state", "null output");
+        LPC_CK(cudaSetDevice(device));
+        if (algo == LPC_ALGO_ADMM) {
+            const T* src = nullptr;
+            switch (which) {
+                case LPC_STATE_IMAGE_EST: src = VH; break;
+                case LPC_STATE_FORWARD: src = VH + (int64_t)Np * plane; break;
+                case LPC_STATE_XI: src = AX + (int64_t)Np * plane; break;
+                case LPC_STATE_RHO: src = rho; break;
+                case LPC_STATE_ETA0: src = eta[eta_cur]; break;
+                case LPC_STATE_ETA1: src = eta[eta_cur] + (int64_t)Np * plane; break;
+                default: return fail(LPC_EINVAL, "get_state", "unknown selector");
+            }
+            return unpack(src, plane, Wp, 0, 0, (T*)dev_out, B * D, Hp, Wp, 0, st);
+        }
+        if (algo >= LPC_ALGO_GD && which == LPC_STATE_IMAGE_EST)
+            return unpack(xpad, plane, Wp, sy, sx, (T*)dev_out, B * D, h, w, 0, st);
+        return fail(LPC_EINVAL, "get_state", "selector not available for this algorithm");
+    }
+    int get_H(void* dev_out, cudaStream_t st) override {
+        if (!psf_set) return fail(LPC_ESTATE, "get_H", "PSF not set");
+        LPC_CK(cudaSetDevice(device));
+        k_unpack_complex<T><<<1184, 256, 0, st>>>(Hc, (Cplx*)dev_out, D, C, Hp, Nh);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+    int get_alpha(void* dev_out, cudaStream_t st) override {
+        if (!psf_set) return fail(LPC_ESTATE, "get_alpha", "PSF not set");
+        LPC_CK(cudaSetDevice(device));
+        LPC_CK(cudaMemcpyAsync(dev_out, consts + 3 * C, C * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        return LPC_OK;
+    }
+
+    // ---------------------------------------------------------------- bare operator
+    int convolve(const void* dev_in, const int64_t* in_strides, void* dev_out, int adjoint, int pad,
+                 cudaStream_t st) override {
+        if (algo != LPC_ALGO_CONV) return fail(LPC_ESTATE, "convolve", "not a convolver plan");
+        if (!psf_set) return fail(LPC_ESTATE, "convolve", "PSF not set");
+        if (!dev_in || !dev_out) return fail(LPC_EINVAL, "convolve", "null pointer");
+        LPC_CK(cudaSetDevice(device));
+        int rc;
+        const int hh = pad ? h : Hp, ww = pad ? w : Wp, oy = pad ? sy : 0, ox = pad ? sx : 0;
+        if (pad && xpad_border_dirty) {
+            LPC_CK(cudaMemsetAsync(xpad, 0, (size_t)Np * plane * sizeof(T), st));
+            xpad_border_dirty = false;
+        }
+        if (!pad) xpad_border_dirty = true;
+        Strides5 ss = in_strides ? from_array(in_strides) : contiguous(D, hh, ww, C);
+        if ((rc = pack((const T*)dev_in, ss, nullptr, Strides5{}, xpad, B, D, hh, ww, plane, Wp, oy, ox, st))) return rc;
+        LPC_CF(cufftSetStream(fwd, st));
+        LPC_CF(cufftSetStream(inv, st));
+        LPC_CF(FftTraits<T>::fwd(fwd, xpad, spec));
+        if ((rc = spec_mul(spec, Np, adjoint, st))) return rc;
+        LPC_CF(FftTraits<T>::inv(inv, spec, rpad));
+        return unpack(rpad, plane, Wp, oy, ox, (T*)dev_out, B * D, hh, ww, 0, st);
+    }
+
+    // ---------------------------------------------------------------- introspection
+    int bytes_per_iter(double* out) override {
+        const double P = (double)sizeof(T) * Np * (double)plane;
+        const double Sp = 2.0 * sizeof(T) * Np * (double)splane;
+        const double d = (double)sizeof(T) * Np * (double)h * w;
+        if (algo == LPC_ALGO_ADMM) *out = 16.0 * P + 9.5 * Sp + d;
+        else if (algo >= LPC_ALGO_GD) *out = 10.0 * d + 6.0 * Sp;
+        else *out = 2.0 * d + 2.0 * Sp;
+        return LPC_OK;
+    }
+    int launches_per_iter(int* total, int* own) override {
+        int o = 0, f = 0;
+        if (algo == LPC_ALGO_ADMM) { o = 2; f = 2; }
+        else if (algo >= LPC_ALGO_GD) { o = 4; f = 4; }
+        else { o = 3; f = 2; }
+        if (own) *own = o;
+        if (total) *total = o + f;  // each cuFFT exec is at least one kernel
+        return LPC_OK;
+    }
+    size_t plan_bytes() override { return total_bytes + work_bytes; }
+};
+
+}  // namespace
+
+// ====================================================================================
+// C-ABI
+// ====================================================================================
+extern "C" {
+
+int lpc_version(void) { return LPC_VERSION; }
+
+const char* lpc_error_name(int code) {
+    switch (code) {
+        case LPC_OK: return "LPC_OK";
+        case LPC_EINVAL: return "LPC_EINVAL";
+        case LPC_ECUDA: return "LPC_ECUDA";
+        case LPC_ECUFFT: return "LPC_ECUFFT";
+        case LPC_ESTATE: return "LPC_ESTATE";
+        case LPC_ENOMEM: return "LPC_ENOMEM";
+        case LPC_ENOTIMPL: return "LPC_ENOTIMPL";
+        default: return "LPC_E?";
+    }
+}
+
+const char* lpc_last_error(lpc_plan_t plan) { return plan ? plan->err.c_str() : g_create_error.c_str(); }
+
+int lpc_next_fast_len(int n) { return next_fast_len_impl(n); }
+
+int lpc_geometry(int h, int w, int* Hp, int* Wp, int* start_y, int* start_x) {
+    if (h <= 0 || w <= 0) return LPC_EINVAL;
+    const int hp = next_fast_len_impl(2 * h - 1), wp = next_fast_len_impl(2 * w - 1);
+    if (Hp) *Hp = hp;
+    if (Wp) *Wp = wp;
+    if (start_y) *start_y = (hp - h) / 2;
+    if (start_x) *start_x = (wp - w) / 2;
+    return LPC_OK;
+}
+
+int lpc_plan_create(lpc_plan_t* out, int device, int algo, int dtype, int norm, int B, int D, int C, int h, int w,
+                    int flags) {
+    if (!out) return LPC_EINVAL;
+    *out = nullptr;
+    auto bad = [&](int code, const char* msg) { g_create_error = std::string(lpc_error_name(code)) + ": " + msg; return code; };
+    if (algo < LPC_ALGO_CONV || algo > LPC_ALGO_FISTA) return bad(LPC_EINVAL, "unknown algorithm");
+    if (dtype != LPC_F32 && dtype != LPC_F64) return bad(LPC_EINVAL, "dtype must be LPC_F32 or LPC_F64 (recon.py:264-290)");
+    if (norm < LPC_NORM_BACKWARD || norm > LPC_NORM_FORWARD) return bad(LPC_EINVAL, "unknown norm");
+    if (C != 1 && C != 3) return bad(LPC_EINVAL, "PSF must either be rgb (3) or grayscale (1) (recon.py:256)");
+    if (B < 1 || D < 1 || h < 1 || w < 1) return bad(LPC_EINVAL, "B, D, h, w must be >= 1");
+    if ((int64_t)B * D * C > 65535) return bad(LPC_EINVAL, "B*D*C must be <= 65535 planes per plan");
+    if (flags & LPC_FLAG_LITERAL) return bad(LPC_ENOTIMPL, "LPC_FLAG_LITERAL (6-FFT debug order) is not built yet");
+    lpc_plan_s* p = nullptr;
+    if (dtype == LPC_F32) p = new (std::nothrow) Plan<float>();
+    else p = new (std::nothrow) Plan<double>();
+    if (!p) return bad(LPC_ENOMEM, "host allocation failed");
+    p->device = device; p->algo = algo; p->dtype = dtype; p->norm = norm;
+    p->B = B; p->D = D; p->C = C; p->h = h; p->w = w; p->flags = flags;
+    int rc = p->init();
+    if (rc != LPC_OK) {
+        g_create_error = p->err;
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return LPC_OK;
+}
+
+int lpc_plan_destroy(lpc_plan_t plan) {
+    delete plan;
+    return LPC_OK;
+}
+
+#define LPC_NEED(plan) \
+    if (!(plan)) return LPC_EINVAL
+
+int lpc_set_psf(lpc_plan_t plan, const void* dev_psf, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_psf(dev_psf, (cudaStream_t)stream);
+}
+int lpc_set_admm_params(lpc_plan_t plan, double mu1, double mu2, double mu3, double tau, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_admm_params(mu1, mu2, mu3, tau, (cudaStream_t)stream);
+}
+int lpc_set_gd_params(lpc_plan_t plan, double lip_fact, double nesterov_mu, double fista_tk, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_gd_params(lip_fact, nesterov_mu, fista_tk, (cudaStream_t)stream);
+}
+int lpc_set_data(lpc_plan_t plan, const void* dev_data, int Dd, const int64_t* strides, const void* dev_background,
+                 const int64_t* bg_strides, void* dev_echo, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_data(dev_data, Dd, strides, dev_background, bg_strides, dev_echo, (cudaStream_t)stream);
+}
+int lpc_set_data_host(lpc_plan_t plan, const void* host_data, int Dd, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_data_host(host_data, Dd, (cudaStream_t)stream);
+}
+int lpc_reset(lpc_plan_t plan, const void* dev_initial_est, void* stream) {
+    LPC_NEED(plan);
+    return plan->reset(dev_initial_est, (cudaStream_t)stream);
+}
+int lpc_run(lpc_plan_t plan, int n_iter, void* stream) {
+    LPC_NEED(plan);
+    return plan->run(n_iter, (cudaStream_t)stream);
+}
+int lpc_get_image(lpc_plan_t plan, void* dev_out, void* stream) {
+    LPC_NEED(plan);
+    return plan->get_image(dev_out, (cudaStream_t)stream);
+}
+int lpc_get_image_host(lpc_plan_t plan, void* host_out, void* stream) {
+    LPC_NEED(plan);
+    return plan->get_image_host(host_out, (cudaStream_t)stream);
+}
+int lpc_get_state(lpc_plan_t plan, int which, void* dev_out, void* stream) {
+    LPC_NEED(plan);
+    return plan->get_state(which, dev_out, (cudaStream_t)stream);
+}
+int lpc_get_H(lpc_plan_t plan, void* dev_out, void* stream) {
+    LPC_NEED(plan);
+    return plan->get_H(dev_out, (cudaStream_t)stream);
+}
+int lpc_get_alpha(lpc_plan_t plan, void* dev_out, void* stream) {
+    LPC_NEED(plan);
+    return plan->get_alpha(dev_out, (cudaStream_t)stream);
+}
+int lpc_convolve(lpc_plan_t plan, const void* dev_in, const int64_t* in_strides, void* dev_out, int adjoint, int pad,
+                 void* stream) {
+    LPC_NEED(plan);
+    return plan->convolve(dev_in, in_strides, dev_out, adjoint, pad, (cudaStream_t)stream);
+}
+int lpc_bytes_per_iter(lpc_plan_t plan, double* algorithmic_bytes) {
+    LPC_NEED(plan);
+    if (!algorithmic_bytes) return LPC_EINVAL;
+    return plan->bytes_per_iter(algorithmic_bytes);
+}
+int lpc_launches_per_iter(lpc_plan_t plan, int* total, int* own) {
+    LPC_NEED(plan);
+    return plan->launches_per_iter(total, own);
+}
+int lpc_profile(lpc_plan_t plan, int n_iter, void* stream, double* phase_ms, int* n_phases) {
+    LPC_NEED(plan);
+    if (!phase_ms || !n_phases || n_iter < 1) return LPC_EINVAL;
+    return plan->profile(n_iter, (cudaStream_t)stream, phase_ms, n_phases);
+}
+const char* lpc_phase_name(int algo, int phase) {
+    static const char* admm[] = {"admm_spatial(K1)", "cufft_r2c", "admm_spectral(K2)", "cufft_c2r"};
+    static const char* gd[] = {"cufft_r2c", "spec_mul_H", "cufft_c2r", "residual", "cufft_r2c", "spec_mul_Hadj", "cufft_c2r", "update"};
+    if (algo == LPC_ALGO_ADMM && phase >= 0 && phase < 4) return admm[phase];
+    if (algo >= LPC_ALGO_GD && algo <= LPC_ALGO_FISTA && phase >= 0 && phase < 8) return gd[phase];
+    return "";
+}
+int lpc_plan_bytes(lpc_plan_t plan, size_t* bytes) {
+    LPC_NEED(plan);
+    if (!bytes) return LPC_EINVAL;
+    *bytes = plan->plan_bytes();
+    return LPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,425 @@
+"""
+GPU mirror of ``lensless.recon.recon.ReconstructionAlgorithm``
+(reference: lensless/recon/recon.py:179-653).
+
+Same constructor / ``set_data`` / ``apply`` / ``reset`` / ``get_image_estimate``
+surface, so the callers in scripts/recon/admm.py, scripts/recon/gradient_descent.py,
+profile/admm.py, profile/gradient_descent.py and lensless/eval/benchmark.py work
+unchanged with a CUDA PSF.  All arithmetic of the iteration loop runs in
+liblpc.so (hand-written sm_100a kernels + cuFFT) on a private planar state; this
+class only holds torch tensors and passes raw device pointers.
+
+Deliberate deviations from the reference, each also in DESIGN.md:
+
+* CUDA tensors only; numpy / CPU tensors raise ``TypeError`` (no CPU fallback).
+* ``apply`` returns a FRESH tensor, not a view into solver state, and does not
+  clamp the ADMM iterate in place (reference quirks i/ii).  A user-supplied
+  ``initial_est`` is never mutated (quirk iii).
+* batch extension: ``set_data`` accepts ``[B, D, h, w, C]`` with B > 1 (the
+  reference asserts B == 1 in ``apply``, recon.py:549-551); ``apply`` then returns
+  ``[B, D, h, w, C]``.  With B == 1 the return is ``[D, h, w, C]`` as in the reference.
+* ``denoiser`` (plug-and-play) and custom ``proj`` / ``psi`` callables are not
+  fusable and raise ``NotImplementedError``.
+"""
+import abc
+import ctypes
+import pathlib as plib
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._engine import EngineStream, torch_dtype_code
+from .rfft_convolve import RealFFTConvolve2D
+
+
+def get_dtype(dtype=None, is_torch=True):
+    """utils/io.py:645-674: only None / "float32" / "float64" strings are accepted."""
+    if dtype is None:
+        dtype = "float32"
+    assert dtype == "float32" or dtype == "float64"
+    return torch.float32 if dtype == "float32" else torch.float64
+
+
+class ReconstructionAlgorithm(abc.ABC):
+    _ALGO = None  # LPC_ALGO_* of the subclass
+
+    def __init__(
+        self,
+        psf,
+        dtype=None,
+        pad=True,
+        n_iter=100,
+        initial_est=None,
+        reset=True,
+        denoiser=None,
+        **kwargs,
+    ):
+        super().__init__()
+        if not isinstance(psf, torch.Tensor) or not psf.is_cuda:
+            raise TypeError(
+                "lenslesspicam_b200 needs a CUDA torch.Tensor PSF: the engine has no CPU path "
+                "(for numpy / CPU tensors use the reference's own classes)"
+            )
+        self.is_torch = True
+        # recon.py:255-256
+        assert len(psf.shape) == 4, "PSF must be 4D: (depth, height, width, channels)."
+        assert psf.shape[3] == 3 or psf.shape[3] == 1, "PSF must either be rgb (3) or grayscale (1)"
+        if denoiser is not None:
+            raise NotImplementedError("plug-and-play denoisers are not fused in the B200 engine (SURVEY 8f.4)")
+        self._denoiser = None
+        self._n_iter = n_iter
+        self._npix = np.prod(psf.shape)
+        self._psf_shape = np.array(psf.shape)
+
+        # recon.py:263-277 (dtype is a *string* or None in the reference)
+        tdtype = get_dtype(dtype, True)
+        self._psf = psf.type(tdtype).contiguous()
+        self._dtype = tdtype
+        self._complex_dtype = torch.complex64 if tdtype == torch.float32 else torch.complex128
+        self._device = self._psf.device
+        self._dev_index = self._device.index if self._device.index is not None else torch.cuda.current_device()
+
+        # recon.py:292-299 (unknown kwargs ride along and are ignored, like rfft_convolve.py:27)
+        self._convolver_param = {"dtype": dtype, "pad": pad, **kwargs}
+        self._pad = pad
+        self._norm = kwargs.get("norm", "ortho")
+        if self._norm not in _lib.NORMS:
+            raise ValueError(f"Invalid norm: {self._norm}")
+        self._convolver_obj = None
+        lib = _lib.load()
+        Hp, Wp, sy, sx = (ctypes.c_int() for _ in range(4))
+        D, h, w, C = (int(v) for v in self._psf.shape)
+        _lib.check(lib.lpc_geometry(h, w, Hp, Wp, sy, sx))
+        self._padded_shape = [D, Hp.value, Wp.value, C]
+        self._start_idx = np.array([sy.value, sx.value])
+        self._end_idx = self._start_idx + self._psf_shape[-3:-1]
+        if pad:
+            self._image_est_shape = self._psf_shape
+        else:
+            self._image_est_shape = self._padded_shape
+
+        self._stream = EngineStream(self._device)
+        self._plans = {}      # batch size -> lpc_plan_t
+        self._plan = None     # plan of the current batch size
+        self._B = 1
+        self._flags = _lib.FLAG_NO_GRAPH if kwargs.get("no_graph", False) else _lib.FLAG_NONE
+
+        if initial_est is not None:
+            self._set_initial_estimate(initial_est)
+        else:
+            self._initial_est = None
+        self._data = None
+        self._data_sent = False
+
+        # used inside trainable recon in the reference; kept for attribute compatibility
+        self.compensation_branch = None
+        self.compensation_branch_inputs = None
+
+        self._select_plan(1)
+        if reset:
+            self.reset()
+
+    # ------------------------------------------------------------------ plans
+    def _select_plan(self, B):
+        plan = self._plans.get(B)
+        if plan is None:
+            lib = _lib.load()
+            plan = ctypes.c_void_p()
+            D, h, w, C = (int(v) for v in self._psf.shape)
+            _lib.check(
+                lib.lpc_plan_create(
+                    ctypes.byref(plan), self._dev_index, self._ALGO, torch_dtype_code(self._dtype),
+                    _lib.NORMS[self._norm], int(B), D, C, h, w, self._flags,
+                )
+            )
+            self._plans[B] = plan
+            with self._stream as st:
+                self._push_params(plan, st)
+                _lib.check(lib.lpc_set_psf(plan, self._psf.data_ptr(), st), plan)
+        self._plan = plan
+        self._B = B
+        return plan
+
+    @abc.abstractmethod
+    def _push_params(self, plan, stream):
+        """send the algorithm's hyper-parameters to a plan"""
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for plan in self._plans.values():
+                lib.lpc_plan_destroy(plan)
+            self._plans = {}
+        except Exception:
+            pass
+
+    @property
+    def _convolver(self):
+        """RealFFTConvolve2D mirror (built on first use; the solver itself does not need it)."""
+        if self._convolver_obj is None:
+            kw = {k: v for k, v in self._convolver_param.items() if k not in ("dtype", "pad", "no_graph")}
+            self._convolver_obj = RealFFTConvolve2D(self._psf, dtype=self._dtype, pad=self._pad, **kw)
+        return self._convolver_obj
+
+    # ------------------------------------------------------------------ data
+    def set_data(self, data):
+        """recon.py:352-381"""
+        assert isinstance(data, torch.Tensor)
+        assert len(data.shape) >= 3, "Data must be at least 3D: [..., width, height, channel]."
+        assert np.all(self._psf_shape[-3:-1] == np.array(data.shape)[-3:-1]), "PSF and data shape mismatch"
+        if len(data.shape) == 3:
+            self._data = data[None, None, ...]
+        elif len(data.shape) == 4:
+            self._data = data[None, ...]
+        else:
+            self._data = data
+        self._data_sent = False
+
+    def _send_data(self, background=None):
+        data = self._data
+        if not data.is_cuda:
+            raise TypeError("data must be a CUDA tensor on the PSF's device")
+        B, Dd = int(data.shape[0]), int(data.shape[1])
+        D, h, w, C = (int(v) for v in self._psf.shape)
+        if Dd not in (1, D) or int(data.shape[4]) != C:
+            raise ValueError("data depth must be 1 or the PSF depth, and channels must match the PSF")
+        data = data.to(self._dtype)
+        plan = self._select_plan(B)
+        lib = _lib.load()
+        echo = None
+        bg_ptr, bg_strides = None, None
+        if background is not None:
+            bg = background.to(device=self._device, dtype=self._dtype)
+            while bg.dim() < 5:
+                bg = bg[None]
+            bg = bg.expand(B, Dd, h, w, C)
+            bg_ptr, bg_strides = bg.data_ptr(), _lib.strides_arg(bg.stride())
+            echo = torch.empty((B, Dd, h, w, C), dtype=self._dtype, device=self._device)
+        with self._stream as st:
+            _lib.check(
+                lib.lpc_set_data(
+                    plan, data.data_ptr(), Dd, _lib.strides_arg(data.stride()), bg_ptr, bg_strides,
+                    echo.data_ptr() if echo is not None else None, st,
+                ),
+                plan,
+            )
+        if echo is not None:
+            self._data = echo  # recon.py:554-555 overwrites self._data
+        self._data_sent = True
+
+    # ------------------------------------------------------------------ estimates
+    def _check_est(self, image_est):
+        assert isinstance(image_est, torch.Tensor)
+        assert len(image_est.shape) >= 4, "Image estimate must be at least 4D: [..., depth, width, height, channel]."
+        assert np.all(
+            np.array(self._image_est_shape[-3:-1]) == np.array(image_est.shape)[-3:-1]
+        ), f"Image estimate must be of shape (..., width, height, channel): {self._image_est_shape[-3:-1]}"
+        return image_est[None, ...] if len(image_est.shape) == 4 else image_est
+
+    def _set_initial_estimate(self, image_est):
+        """recon.py:383-413 (takes effect at the next reset())"""
+        self._initial_est = self._check_est(image_est)
+
+    def set_image_estimate(self, image_est):
+        """recon.py:415-442: overwrite the current estimate (warm start without touching _initial_est)."""
+        est = self._check_est(image_est)
+        self._reset_plan(est)
+
+    def get_image_estimate(self):
+        """recon.py:444-446 -> [B, D, h, w, C]"""
+        return self._form_image()
+
+    @property
+    def _image_est(self):
+        """Current iterate in the reference's layout (ADMM: padded [B,D,Hp,Wp,C]; GD: [B,D,h,w,C])."""
+        D, Hp, Wp, C = self._padded_shape
+        shape = (self._B, D, Hp, Wp, C) if not self._pad else (self._B,) + tuple(int(v) for v in self._psf.shape)
+        out = torch.empty(shape, dtype=self._dtype, device=self._device)
+        lib = _lib.load()
+        with self._stream as st:
+            _lib.check(lib.lpc_get_state(self._plan, _lib.STATE_IMAGE_EST, out.data_ptr(), st), self._plan)
+        return out
+
+    def _set_psf(self, psf):
+        """recon.py:448-470"""
+        assert psf.shape[-1] == 3 or psf.shape[-1] == 1, "PSF must either be rgb (3) or grayscale (1)"
+        assert self._psf.shape == psf.shape, "new PSF must have same shape as old PSF"
+        assert isinstance(psf, type(self._psf)), "new PSF must have same type as old PSF"
+        self._psf = psf.to(device=self._device, dtype=self._dtype).contiguous()
+        self._convolver_obj = None
+        lib = _lib.load()
+        with self._stream as st:
+            for plan in self._plans.values():
+                _lib.check(lib.lpc_set_psf(plan, self._psf.data_ptr(), st), plan)
+        self.reset()
+
+    # ------------------------------------------------------------------ iteration
+    def _reset_plan(self, initial_est=None):
+        lib = _lib.load()
+        ptr = None
+        if initial_est is not None:
+            est = initial_est.to(device=self._device, dtype=self._dtype)
+            est = est.expand((self._B,) + tuple(est.shape[1:])).contiguous()
+            ptr = est.data_ptr()
+        with self._stream as st:
+            _lib.check(lib.lpc_reset(self._plan, ptr, st), self._plan)
+
+    def reset(self):
+        """Reset state variables (admm.py:150-230 / gd.py:94-126)."""
+        self._reset_plan(self._initial_est)
+
+    def _update(self, iter):
+        """One iteration (recon.py:338-343); ``apply`` runs all of them in one call instead."""
+        lib = _lib.load()
+        with self._stream as st:
+            _lib.check(lib.lpc_run(self._plan, 1, st), self._plan)
+
+    def _form_image(self):
+        """admm.py:331-338 / gd.py:136-140 -> fresh [B, D, h, w, C] tensor."""
+        D, h, w, C = (int(v) for v in self._psf.shape)
+        out = torch.empty((self._B, D, h, w, C), dtype=self._dtype, device=self._device)
+        lib = _lib.load()
+        with self._stream as st:
+            _lib.check(lib.lpc_get_image(self._plan, out.data_ptr(), st), self._plan)
+        return out
+
+    def _progress(self):
+        return
+
+    def _get_numpy_data(self, data):
+        return data.detach().cpu().numpy()
+
+    def apply(
+        self,
+        n_iter=None,
+        disp_iter=-1,
+        plot_pause=0.2,
+        plot=False,
+        save=False,
+        gamma=None,
+        ax=None,
+        reset=True,
+        background=None,
+        **kwargs,
+    ):
+        """recon.py:498-605.  Extra keyword arguments are accepted and ignored
+        (eval/benchmark.py:247-253 passes ``output_intermediate``)."""
+        assert self._data is not None, "Must set data with `set_data()`"
+        if background is not None or not self._data_sent or int(self._data.shape[0]) != self._B:
+            self._send_data(background)
+        if reset:
+            self.reset()
+        if n_iter is None:
+            n_iter = self._n_iter
+
+        lib = _lib.load()
+        if (plot or save) and disp_iter is not None:
+            plot_image, plt = _import_plotting()
+            if ax is None:
+                ax = plot_image(self._get_numpy_data(self._form_image()[0]), gamma=gamma)
+            if disp_iter is None or disp_iter <= 0:
+                disp_iter = n_iter + 1
+            done = 0
+            while done < n_iter:
+                step = min(disp_iter - (done % disp_iter), n_iter - done)
+                with self._stream as st:
+                    _lib.check(lib.lpc_run(self._plan, int(step), st), self._plan)
+                done += step
+                if done % disp_iter == 0:
+                    self._progress()
+                    ax = plot_image(self._get_numpy_data(self._form_image()[0]), ax=ax, gamma=gamma)
+                    title = "Reconstruction after iteration {}".format(done)
+                    (ax[0, 0] if hasattr(ax, "__len__") else ax).set_title(title)
+                    if save:
+                        plt.savefig(plib.Path(save) / f"{done}.png")
+                    if plot:
+                        plt.draw()
+                        plt.pause(plot_pause)
+        else:
+            ax = None
+            with self._stream as st:
+                _lib.check(lib.lpc_run(self._plan, int(n_iter), st), self._plan)
+
+        img = self._form_image()
+        final_im = img[0] if self._B == 1 else img
+        if plot:
+            plot_image, plt = _import_plotting()
+            ax = plot_image(self._get_numpy_data(final_im), ax=ax, gamma=gamma)
+            title = "Final reconstruction after {} iterations".format(n_iter)
+            (ax[0, 0] if hasattr(ax, "__len__") else ax).set_title(title)
+            if save:
+                plt.savefig(plib.Path(save) / f"{n_iter}.png")
+            return final_im, ax
+        return final_im
+
+    def forward(self, batch, psfs=None, background=None):
+        """Batched inference in the shape of ``TrainableReconstructionAlgorithm.forward``
+        (trainable_recon.py:297-405, no learnable parameters): ``[B, D|1, h, w, C] -> [B, D, h, w, C]``."""
+        if psfs is not None:
+            self._set_psf(psfs)
+        self.set_data(batch)
+        out = self.apply(disp_iter=None, plot=False, background=background)
+        return out[None] if self._B == 1 else out
+
+    # ------------------------------------------------------------------ metrics
+    def reconstruction_error(self, prediction=None, lensless=None, psfs=None, normalize=True):
+        """recon.py:607-653.  The convolution runs in the engine; the min/max/sum reductions are
+        torch ops (evaluation-loop work, SURVEY 8f.2 -- outside the iteration hot path)."""
+        if prediction is None:
+            prediction = self.get_image_estimate()
+        if lensless is None:
+            lensless = self._data
+        if psfs is None:
+            psfs = self._psf
+        kw = {k: v for k, v in self._convolver_param.items() if k != "no_graph"}
+        convolver = RealFFTConvolve2D(psfs.to(prediction.device), **kw)
+        if not convolver.pad:
+            prediction = convolver._pad(prediction)
+        Hx = convolver.convolve(prediction)
+        if not convolver.pad:
+            Hx = convolver._crop(Hx)
+        if normalize:
+            Hx = Hx - torch.amin(Hx, dim=(-1, -2, -3), keepdim=True)
+            Hx = Hx / torch.amax(Hx, dim=(-1, -2, -3), keepdim=True)
+        return torch.sum((Hx - lensless) ** 2, dim=(-1, -2, -3, -4)) / self._npix
+
+    # ------------------------------------------------------------------ host-buffer path (bench e2e)
+    def apply_host(self, host_data, host_out, n_iter=None):
+        """End-to-end call with HOST buffers: H2D copy, reset, n_iter iterations, crop/clamp,
+        D2H copy -- all enqueued on one stream; the caller synchronises.  ``host_data`` is
+        ``[B, Dd, h, w, C]`` (pinned recommended), ``host_out`` ``[B, D, h, w, C]``."""
+        assert host_data.dim() == 5 and not host_data.is_cuda and not host_out.is_cuda
+        assert host_data.dtype == self._dtype and host_out.dtype == self._dtype
+        assert host_data.is_contiguous() and host_out.is_contiguous()
+        B, Dd = int(host_data.shape[0]), int(host_data.shape[1])
+        plan = self._select_plan(B)
+        lib = _lib.load()
+        if n_iter is None:
+            n_iter = self._n_iter
+        with self._stream as st:
+            _lib.check(lib.lpc_set_data_host(plan, host_data.data_ptr(), Dd, st), plan)
+            _lib.check(lib.lpc_reset(plan, None, st), plan)
+            _lib.check(lib.lpc_run(plan, int(n_iter), st), plan)
+            _lib.check(lib.lpc_get_image_host(plan, host_out.data_ptr(), st), plan)
+        self._data_sent = False
+        return host_out
+
+    def bytes_per_iter(self):
+        """Algorithmic HBM bytes one iteration moves for the current batch."""
+        lib = _lib.load()
+        v = ctypes.c_double()
+        _lib.check(lib.lpc_bytes_per_iter(self._plan, ctypes.byref(v)), self._plan)
+        return v.value
+
+
+def _import_plotting():
+    try:
+        import matplotlib.pyplot as plt
+        from lensless.utils.plot import plot_image
+    except Exception as e:  # pragma: no cover - matplotlib is not in the image
+        raise ImportError(
+            "plot=True / save=... need matplotlib and the reference's lensless.utils.plot.plot_image "
+            "(visualisation is out of the engine's scope)"
+        ) from e
+    return plot_image, plt

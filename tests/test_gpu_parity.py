@@ -1,0 +1,318 @@
+"""
+Parity of the CUDA engine (through the C-ABI, via the mirror classes) against
+(a) the committed golden outputs of the reference's fp32 torch path and (b) the
+CPU oracle on the same seeded inputs.  Needs a GPU: ``pytest -m gpu``.
+
+Tolerance (north_star): 1e-5 relative for fp32 -- measured as max|ours-ref| / max|ref|;
+pad/crop indexing bit-exact.  FISTA at large iteration counts is gated on the
+fp64 envelope instead: err(ours, fp64) <= 1.5 * err(ref fp32, fp64).
+"""
+import numpy as np
+import pytest
+import torch
+
+import lensless_oracle as orc
+from conftest import load_golden, rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+CASES = ["small_even_rgb", "small_odd_rgb", "small_gray", "small_mixed"]
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)
+
+
+def L():
+    import lenslesspicam_b200
+
+    return lenslesspicam_b200
+
+
+ALGOS = {"admm": "ADMM", "gd": "GradientDescent", "nesterov": "NesterovGradientDescent", "fista": "FISTA"}
+
+
+def run(algo, psf, data, n_iter, dtype="float32", **kw):
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    rec = getattr(L(), ALGOS[algo])(dev(psf, tdt), dtype=dtype, **kw)
+    rec.set_data(dev(data, tdt))
+    res = rec.apply(n_iter=n_iter, disp_iter=None, plot=False)
+    return res, rec
+
+
+# ------------------------------------------------------------------------------ golden parity
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("algo", list(ALGOS))
+def test_parity_with_reference_goldens(case, algo):
+    g = load_golden(case)
+    for n in (1, 5, 30):
+        res, rec = run(algo, g["psf"], g["data"], n)
+        ref = g[f"{algo}_t32_{n}"]
+        # output contract of the reference tests (test_algos.py:110-131)
+        assert res.dtype == torch.float32 and tuple(res.shape) == ref.shape and res.is_cuda
+        assert rec._n_iter == 100
+        out = res.cpu().numpy()
+        assert (out >= 0).all()
+        assert rel_to_max(out, ref) <= TOL, (case, algo, n, rel_to_max(out, ref))
+        # envelope against fp64 truth: no worse than 1.5x the reference's own fp32 error (+ tiny floor)
+        truth = g[f"{algo}_t64_{n}"]
+        assert rel_to_max(out, truth) <= 1.5 * rel_to_max(ref, truth) + 2e-7, (case, algo, n)
+
+
+@pytest.mark.parametrize("algo", list(ALGOS))
+def test_parity_fp64(algo):
+    g = load_golden("small_odd_rgb")
+    res, _ = run(algo, g["psf"], g["data"], 30, dtype="float64")
+    assert res.dtype == torch.float64
+    assert rel_to_max(res.cpu().numpy(), g[f"{algo}_t64_30"]) <= 1e-10
+
+
+def test_parity_bundled_data():
+    """the reference's bundled tape PSF / thumbs-up measurement (load_data(downsample=16))"""
+    g = load_golden("bundled_ds16")
+    for n in (5, 100):
+        res, _ = run("admm", g["psf"], g["data"], n)
+        assert rel_to_max(res.cpu().numpy(), g[f"admm_t32_{n}"]) <= TOL
+    res, _ = run("fista", g["psf"], g["data"], 20)
+    assert rel_to_max(res.cpu().numpy(), g["fista_t32_20"]) <= TOL
+
+
+def test_variants():
+    g = load_golden("variants")
+    kw = dict(mu1=3e-6, mu2=2e-5, mu3=1e-4, tau=3e-4)
+    res, _ = run("admm", g["psf"], g["data"], 10, **kw)
+    assert rel_to_max(res.cpu().numpy(), g["admm_params_t32_10"]) <= TOL
+    # warm start with a padded-shape initial estimate (recon.py:296-299; admm.py:154-155,172-176)
+    init = dev(g["init"])
+    keep = init.clone()
+    res, _ = run("admm", g["psf"], g["data"], 10, initial_est=init)
+    assert rel_to_max(res.cpu().numpy(), g["admm_init_t32_10"]) <= TOL
+    assert torch.equal(init, keep), "initial_est must not be mutated"
+    # background subtraction + clamp (recon.py:553-555)
+    rec = L().ADMM(dev(g["psf"]))
+    rec.set_data(dev(g["data"]))
+    res = rec.apply(n_iter=5, disp_iter=None, plot=False, background=dev(g["bg"]))
+    assert rel_to_max(res.cpu().numpy(), g["admm_bg_t32_5"]) <= TOL
+    expect = np.maximum(g["data"][None] - g["bg"][None], 0)
+    assert np.array_equal(rec._data.cpu().numpy(), expect)  # self._data is overwritten, recon.py:554
+    # FISTA with tk != 1 exercises the first-iteration aliasing quirk (gd.py:233,236)
+    res, _ = run("fista", g["psf"], g["data"], 10, tk=2.0, lip_fact=1.2)
+    assert rel_to_max(res.cpu().numpy(), g["fista_params_t32_10"]) <= TOL
+
+
+def test_continuation_is_exact():
+    """apply(5) + apply(5, reset=False) == apply(10).  (The reference clamps V in place when it
+    forms the image, so ITS continuation differs from its own 10-iteration run; the engine
+    returns a fresh tensor and keeps the iterate -- documented deviation.)"""
+    g = load_golden("variants")
+    a, _ = run("admm", g["psf"], g["data"], 10)
+    rec = L().ADMM(dev(g["psf"]))
+    rec.set_data(dev(g["data"]))
+    rec.apply(n_iter=5, disp_iter=None)
+    b = rec.apply(n_iter=5, disp_iter=None, reset=False)
+    assert torch.equal(a, b)
+    for algo in ("gd", "nesterov", "fista"):
+        a, _ = run(algo, g["psf"], g["data"], 9)
+        rec = getattr(L(), ALGOS[algo])(dev(g["psf"]))
+        rec.set_data(dev(g["data"]))
+        rec.apply(n_iter=4, disp_iter=None)
+        b = rec.apply(n_iter=5, disp_iter=None, reset=False)
+        assert torch.equal(a, b), algo
+
+
+def test_repeated_apply_is_reproducible():
+    g = load_golden("small_even_rgb")
+    rec = L().FISTA(dev(g["psf"]))
+    rec.set_data(dev(g["data"]))
+    a = rec.apply(n_iter=7, disp_iter=None)
+    b = rec.apply(n_iter=7, disp_iter=None)  # reset restores tk (gd.py:227-233); graph replay path
+    assert torch.equal(a, b)
+    rec = L().ADMM(dev(g["psf"]))
+    rec.set_data(dev(g["data"]))
+    a = rec.apply(n_iter=7, disp_iter=None)
+    b = rec.apply(n_iter=7, disp_iter=None)
+    c = rec.apply(n_iter=7, disp_iter=None)
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_graph_and_plain_launches_agree():
+    g = load_golden("small_odd_rgb")
+    for algo in ALGOS:
+        a, _ = run(algo, g["psf"], g["data"], 6)
+        b, _ = run(algo, g["psf"], g["data"], 6, no_graph=True)
+        assert torch.equal(a, b), algo
+
+
+def test_depth_gd():
+    """3-D PSF: D independent planes sharing alpha and x0, measurement broadcast over depth"""
+    g = load_golden("depth_gd")
+    for algo in ("gd", "fista"):
+        res, _ = run(algo, g["psf"], g["data"], 10)
+        assert tuple(res.shape) == (4, 16, 20, 3)
+        assert rel_to_max(res.cpu().numpy(), g[f"{algo}_t32_10"]) <= TOL
+
+
+def test_admm_depth_is_refused_like_the_reference():
+    with pytest.raises(NotImplementedError):
+        L().ADMM(torch.rand(2, 8, 8, 3, device="cuda"))
+
+
+def test_admm_depth_extension_equals_independent_planes():
+    g = load_golden("depth_gd")
+    psf, data = g["psf"], g["data"]
+    rec = L().ADMM(dev(psf), allow_depth=True)
+    rec.set_data(dev(data))
+    full = rec.apply(n_iter=8, disp_iter=None).cpu().numpy()
+    assert full.shape == (4, 16, 20, 3)
+    for d in range(4):
+        one = orc.reconstruct("admm", psf[d : d + 1], data, 8)
+        assert rel_to_max(full[d : d + 1], one) <= TOL
+
+
+def test_batch_matches_per_sample_and_unrolled():
+    g = load_golden("batch")
+    rec = L().ADMM(dev(g["psf"]), n_iter=10)
+    out = rec.forward(dev(g["batch"]))
+    assert tuple(out.shape) == (4, 1, 24, 32, 3)
+    out = out.cpu().numpy()
+    assert rel_to_max(out, g["admm_t32_10"]) <= TOL
+    assert rel_to_max(out, g["unrolled_admm_t32_10"]) <= TOL
+    # a batched run equals its own single-sample runs (planes are independent)
+    for b in range(4):
+        rec.set_data(dev(g["batch"][b]))
+        one = rec.apply(disp_iter=None)
+        assert rel_to_max(one.cpu().numpy(), out[b]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------ live oracle parity
+@pytest.mark.parametrize("shape", [(135, 240, 3), (203, 61, 3), (100, 136, 1)])
+def test_parity_with_oracle_mid_size(shape):
+    """BASELINE config 1's ~3x135x240 class, an odd-padded shape and a gray one, seeded inputs"""
+    h, w, C = shape
+    psf, data = orc.synthetic_problem(h, w, C, seed=11)
+    for algo, n in (("admm", 20), ("fista", 20), ("gd", 10), ("nesterov", 10)):
+        res, _ = run(algo, psf, data, n)
+        ref = orc.reconstruct(algo, psf, data, n)
+        assert rel_to_max(res.cpu().numpy(), ref) <= TOL, (shape, algo, rel_to_max(res.cpu().numpy(), ref))
+
+
+def test_generic_and_vector_spatial_kernel_widths():
+    """Wp % 4 == 0 takes the 128-bit vector kernel, anything else the generic one: widths 27 / 45
+    pad to 54 / 90 (generic), 32 / 40 pad to 64 / 80 (vector; 80/4 = 20 vectors < one warp)."""
+    for w in (27, 45, 32, 40):
+        psf, data = orc.synthetic_problem(24, w, 3, seed=5)
+        res, _ = run("admm", psf, data, 15)
+        assert rel_to_max(res.cpu().numpy(), orc.reconstruct("admm", psf, data, 15)) <= TOL
+
+
+# ------------------------------------------------------------------------------ convolver
+def test_convolver_matches_reference():
+    g = load_golden("convolver")
+    Lp = L()
+    for norm in ("ortho", "backward"):
+        c = Lp.RealFFTConvolve2D(dev(g["psf"]), pad=True, norm=norm)
+        assert list(c._padded_shape) == list(g["padded_shape"])
+        assert list(c._start_idx) == list(g["start"])
+        assert rel_to_max(c.convolve(dev(g["data"])).cpu().numpy(), g[f"conv_{norm}"]) <= TOL
+        assert rel_to_max(c.deconvolve(dev(g["data"])).cpu().numpy(), g[f"deconv_{norm}"]) <= TOL
+        # depth-1 data broadcast against a depth-5 PSF (test_convolver.py:43-49)
+        assert rel_to_max(c.convolve(dev(g["data_d1"])).cpu().numpy(), g[f"conv_d1_{norm}"]) <= TOL
+    c = Lp.RealFFTConvolve2D(dev(g["psf"]), pad=True, norm="ortho")
+    H = c._H.cpu().numpy()
+    assert H.shape == g["H_ortho"].shape and rel_to_max(H, g["H_ortho"]) <= TOL
+    c2 = Lp.RealFFTConvolve2D(dev(g["psf"]), pad=False, norm="backward")
+    padded = c2._pad(dev(g["data"]))
+    assert rel_to_max(c2.convolve(padded).cpu().numpy(), g["conv_nopad"]) <= TOL
+    assert rel_to_max(c2.deconvolve(padded).cpu().numpy(), g["deconv_nopad"]) <= TOL
+
+
+def test_pad_crop_bit_exact():
+    """test_convolver.py:11-28"""
+    psf = torch.rand(5, 47, 29, 3, device="cuda")
+    c = L().RealFFTConvolve2D(psf, pad=True)
+    data = torch.rand(12, 5, 47, 29, 3, device="cuda")
+    padded = c._pad(data)
+    np.testing.assert_array_equal(padded.shape[1:], c._padded_shape)
+    assert torch.equal(c._crop(padded), data)
+    # and the engine's own pack/unpack: identity PSF (delta at the centre tap) returns the input window
+    # exactly up to FFT round-off, and zero input gives exactly zero
+    z = c.convolve(torch.zeros(1, 5, 47, 29, 3, device="cuda"))
+    assert torch.count_nonzero(z) == 0
+
+
+def test_conv_slice_independence():
+    """test_convolver.py:32-59: one (batch, depth) slice alone equals the slice of the full result"""
+    psf = torch.rand(5, 47, 29, 3, device="cuda")
+    c = L().RealFFTConvolve2D(psf, pad=True)
+    data = torch.rand(6, 1, 47, 29, 3, device="cuda")
+    full = c.convolve(data)
+    part = c.convolve(data[:1, :1])
+    torch.testing.assert_close(full[:1], part)
+    # single channel against an RGB PSF broadcasts over channels (test_convolver.py:32-40)
+    part1 = c.convolve(data[:1, :1, :, :, :1])
+    torch.testing.assert_close(full[:1, :, :, :, :1], part1[:1, :, :, :, :1])
+
+
+# ------------------------------------------------------------------------------ boundary behaviour
+def test_constructor_tolerates_hydra_kwargs_and_set_initial_est():
+    """scripts/recon/admm.py:78 passes unknown keys; test_algos.py:39-60"""
+    g = load_golden("small_even_rgb")
+    psf = dev(g["psf"])
+    rec = L().ADMM(psf, n_iter=3, unrolled=False, checkpoint_fp=None, pre_process_model=None, post_process_model=None)
+    rec.set_data(dev(g["data"]))
+    res = rec.apply(disp_iter=None, plot=False, output_intermediate=False)
+    assert rel_to_max(res.cpu().numpy(), run("admm", g["psf"], g["data"], 3)[0].cpu().numpy()) == 0
+    assert list(rec._image_est_shape) == [1, 48, 64, 3]
+    est = torch.rand(1, 48, 64, 3, device="cuda")
+    rec._set_initial_estimate(est)
+    assert torch.equal(rec._initial_est, est[None])
+    rec2 = L().FISTA(psf, initial_est=torch.rand(1, 24, 32, 3, device="cuda"))
+    assert tuple(rec2._initial_est.shape) == (1, 1, 24, 32, 3)
+    with pytest.raises(AssertionError):
+        rec.set_data(torch.rand(1, 10, 10, 3, device="cuda"))
+    with pytest.raises(AssertionError):
+        L().ADMM(psf).apply()  # data not set (recon.py:548)
+
+
+def test_set_psf_and_reconstruction_error():
+    g = load_golden("small_even_rgb")
+    g2 = load_golden("variants")
+    rec = L().ADMM(dev(g["psf"]))
+    rec.set_data(dev(g2["data"]))
+    rec.apply(n_iter=2, disp_iter=None)
+    rec._set_psf(dev(g2["psf"]))  # benchmark.py:245
+    res = rec.apply(n_iter=10, disp_iter=None)
+    ref = orc.reconstruct("admm", g2["psf"], g2["data"], 10)
+    assert rel_to_max(res.cpu().numpy(), ref) <= TOL
+    err = rec.reconstruction_error()
+    assert err.shape == (1,) and torch.isfinite(err).all()
+
+
+def test_host_buffer_path_matches_device_path():
+    g = load_golden("small_even_rgb")
+    rec = L().ADMM(dev(g["psf"]))
+    host_in = torch.from_numpy(g["data"][None]).pin_memory()
+    host_out = torch.empty(1, 1, 24, 32, 3).pin_memory()
+    rec.apply_host(host_in, host_out, n_iter=5)
+    torch.cuda.synchronize()
+    a, _ = run("admm", g["psf"], g["data"], 5)
+    assert np.array_equal(host_out[0].numpy(), a.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------ full size (BASELINE configs[1])
+def test_full_size_admm_against_oracle_and_properties():
+    """3x1080x1920 (padded 2160x3840): two ADMM iterations against the CPU oracle (~15 s of numpy),
+    then size-independent properties at 10 iterations: channel independence and batch == single."""
+    psf, data = orc.synthetic_problem(1080, 1920, 3, seed=0)
+    res, rec = run("admm", psf, data, 2)
+    ref = orc.reconstruct("admm", psf, data, 2, workers=8)
+    assert rel_to_max(res.cpu().numpy(), ref) <= TOL
+    full = rec.apply(n_iter=10, disp_iter=None)
+    gray, _ = run("admm", psf[..., 1:2], data[..., 1:2], 10)
+    assert rel_to_max(gray.cpu().numpy(), full[..., 1:2].cpu().numpy()) <= 1e-6
+    rec._n_iter = 10
+    both = rec.forward(torch.stack([dev(data), dev(data[:, ::-1].copy())]))
+    rec.set_data(dev(data))
+    assert torch.equal(rec.apply(n_iter=10, disp_iter=None), full)
+    assert rel_to_max(both[0].cpu().numpy(), full.cpu().numpy()) <= 1e-6
