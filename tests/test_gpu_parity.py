@@ -302,17 +302,29 @@ def test_host_buffer_path_matches_device_path():
 
 # ------------------------------------------------------------------------------ full size (BASELINE configs[1])
 def test_full_size_admm_against_oracle_and_properties():
-    """3x1080x1920 (padded 2160x3840): two ADMM iterations against the CPU oracle (~15 s of numpy),
-    then size-independent properties at 10 iterations: channel independence and batch == single."""
+    """3x1080x1920 (padded 2160x3840): two ADMM iterations against the CPU oracle in fp32 AND fp64
+    (~25 s of numpy), then size-independent properties at 10 iterations.
+
+    At this size the reference's own fp32 arithmetic is 1.9e-5 (rel-to-max) away from its fp64
+    result after two iterations (measured with the oracle, which follows the reference operation
+    by operation; see DESIGN.md "Tolerance at full size"), so no independent fp32 implementation
+    can sit within 1e-5 of it.  The gate is therefore: ours within 1e-5 of the fp64 truth, and the
+    distance to the fp32 reference explained by the reference's own error."""
     psf, data = orc.synthetic_problem(1080, 1920, 3, seed=0)
     res, rec = run("admm", psf, data, 2)
-    ref = orc.reconstruct("admm", psf, data, 2, workers=8)
-    assert rel_to_max(res.cpu().numpy(), ref) <= TOL
+    out = res.cpu().numpy()
+    ref32 = orc.reconstruct("admm", psf, data, 2, workers=8)
+    ref64 = orc.reconstruct("admm", psf.astype(np.float64), data.astype(np.float64), 2, dtype="float64", workers=8)
+    e_ours, e_ref = rel_to_max(out, ref64), rel_to_max(ref32, ref64)
+    print(f"full size ADMM-2: ours vs fp64 {e_ours:.2e}; reference fp32 vs fp64 {e_ref:.2e}; ours vs fp32 {rel_to_max(out, ref32):.2e}")
+    assert e_ours <= TOL
+    assert e_ours <= e_ref
+    assert rel_to_max(out, ref32) <= e_ref + e_ours + 1e-7
     full = rec.apply(n_iter=10, disp_iter=None)
     gray, _ = run("admm", psf[..., 1:2], data[..., 1:2], 10)
-    assert rel_to_max(gray.cpu().numpy(), full[..., 1:2].cpu().numpy()) <= 1e-6
+    assert rel_to_max(gray.cpu().numpy(), full[..., 1:2].cpu().numpy()) <= 1e-6  # channel independence
     rec._n_iter = 10
     both = rec.forward(torch.stack([dev(data), dev(data[:, ::-1].copy())]))
     rec.set_data(dev(data))
-    assert torch.equal(rec.apply(n_iter=10, disp_iter=None), full)
-    assert rel_to_max(both[0].cpu().numpy(), full.cpu().numpy()) <= 1e-6
+    assert torch.equal(rec.apply(n_iter=10, disp_iter=None), full)  # reproducible after a batch-2 detour
+    assert rel_to_max(both[0].cpu().numpy(), full.cpu().numpy()) <= 1e-6  # batch == single
