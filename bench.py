@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--engine", default=None, choices=[None, "v1"], help="v1 = K1/K2 + cuFFT (A/B against the fused engine)")
     return ap.parse_args()
 
 
@@ -240,7 +241,7 @@ def main():
     cls = L.ADMM if args.algo == "admm" else L.FISTA
     stream = torch.cuda.Stream(device=device)
     with torch.cuda.stream(stream):
-        recon = cls(psf, n_iter=n_iter, no_graph=args.no_graph)
+        recon = cls(psf, n_iter=n_iter, no_graph=args.no_graph, engine=args.engine)
 
         def step_device():
             recon.set_data(meas)
@@ -290,7 +291,7 @@ def main():
         algo_code = _lib.ALGO_ADMM if args.algo == "admm" else _lib.ALGO_FISTA
         phases = {}
         for i in range(nph.value):
-            name = lib.lpc_phase_name(algo_code, i).decode()
+            name = lib.lpc_phase_name(recon._plan, i).decode()
             phases[name] = phases.get(name, 0.0) + phase_ms[i]
         bytes_iter = recon.bytes_per_iter()
 
@@ -309,13 +310,21 @@ def main():
     P = 4.0 * Bg * Hp * Wp * C
     Sp = 8.0 * Bg * Hp * (Wp // 2 + 1) * C
     d = 4.0 * Bg * h * w * C
+    # algorithmic bytes of OUR kernels, per launch
+    kernel_bytes = {
+        "admm_spatial(K1)": 11.0 * P + d,        # v1: reads V,HV,xi',rho',eta'0,eta'1 (+y); writes xi',rho',eta'0,eta'1,a
+        "admm_spectral(K2)": 5.5 * Sp,           # v1: reads A,Xi,H,R; writes Vhat,HVhat
+        "admm_rows(B)": 8.0 * P + 4.0 * Sp + d,  # v2: reads Tin(2Sp),xi',rho',eta'(2P) (+y); writes the same 4P and Tout(2Sp)
+        "admm_cols(A)": 5.5 * Sp,                # v2: reads Tout(2Sp),H,R; writes Tin(2Sp)
+        "update": 5.0 * d, "residual": 3.0 * d, "spec_mul_H": 3.0 * Sp, "spec_mul_Hadj": 3.0 * Sp,
+    }
+    own = {n: t for n, t in phases.items() if n in kernel_bytes}
+    kname = max(own, key=own.get)  # our dominant kernel = the one with the longest launch
+    kbytes = kernel_bytes[kname]
+    engine = lib.lpc_engine_version(recon._plan)
     if args.algo == "admm":
-        kname = "admm_spatial(K1)"
-        kbytes = 11.0 * P + d  # reads V,HV,xi',rho',eta'0,eta'1 (+ y in the window); writes xi',rho',eta'0,eta'1,a
-        own_launches = 2 * n_iter + 2  # K1+K2 per iteration, pack + unpack per recon
+        own_launches = 2 * n_iter + 2 + (1 if engine == 2 else 0)  # 2 kernels / iteration, pack + unpack (+ row IFFT) per recon
     else:
-        kname = "update"
-        kbytes = 5.0 * d
         own_launches = 4 * n_iter + 3
     k_ms = phases.get(kname, 0.0)
     achieved = kbytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
@@ -325,6 +334,8 @@ def main():
         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kbytes, "launch_ms": k_ms,
         "phases_ms_per_iter": phases,
+        "phases_GBs": {n: kernel_bytes[n] / (t * 1e-3) / 1e9 for n, t in own.items() if t > 0},
+        "engine": "v2 fused own-FFT (2 kernels / iteration)" if engine == 2 else "v1 K1/K2 + cuFFT",
         "iteration": {
             "algorithmic_bytes": bytes_iter, "ms_ungraphed": iter_ms, "ms_in_step": ms_step / n_iter / Bg,
             "achieved_GBs": bytes_iter / (ms_step / n_iter * 1e-3) / 1e9,

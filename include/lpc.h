@@ -74,6 +74,7 @@ extern "C" {
 #define LPC_FLAG_NONE 0
 #define LPC_FLAG_NO_GRAPH 1   /* never capture the iteration loop in a CUDA graph        */
 #define LPC_FLAG_LITERAL 2    /* debug: reference's literal 6-FFT ADMM order (bisecting) */
+#define LPC_FLAG_ENGINE_V1 4  /* ADMM: K1/K2 + cuFFT engine instead of the fused own-FFT engine  */
 
 typedef struct lpc_plan_s* lpc_plan_t;
 
@@ -167,7 +168,9 @@ int lpc_launches_per_iter(lpc_plan_t plan, int* total, int* own);
  * iteration with CUDA events on `stream`; returns the mean device time (ms) of each
  * phase in phase_ms[0..*n_phases) (at most 8).  Synchronises.  Names: lpc_phase_name. */
 int lpc_profile(lpc_plan_t plan, int n_iter, void* stream, double* phase_ms, int* n_phases);
-const char* lpc_phase_name(int algo, int phase);
+const char* lpc_phase_name(lpc_plan_t plan, int phase);
+/* 2 = fused own-FFT engine (lpc_fused.cuh), 1 = K1/K2 + cuFFT */
+int lpc_engine_version(lpc_plan_t plan);
 /* device bytes held by the plan */
 int lpc_plan_bytes(lpc_plan_t plan, size_t* bytes);
 

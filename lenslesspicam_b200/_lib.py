@@ -19,7 +19,7 @@ ALGO_CONV, ALGO_ADMM, ALGO_GD, ALGO_NESTEROV, ALGO_FISTA = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 NORMS = {"backward": 0, "ortho": 1, "forward": 2}
 STATE_IMAGE_EST, STATE_FORWARD, STATE_XI, STATE_RHO, STATE_ETA0, STATE_ETA1 = range(6)
-FLAG_NONE, FLAG_NO_GRAPH = 0, 1
+FLAG_NONE, FLAG_NO_GRAPH, FLAG_LITERAL, FLAG_ENGINE_V1 = 0, 1, 2, 4
 
 _lock = threading.Lock()
 _lib = None
@@ -55,7 +55,8 @@ PROTOTYPES = {
     "lpc_bytes_per_iter": (_i, [_vp, ctypes.POINTER(_d)]),
     "lpc_launches_per_iter": (_i, [_vp, _ip, _ip]),
     "lpc_profile": (_i, [_vp, _i, _vp, ctypes.POINTER(_d), _ip]),
-    "lpc_phase_name": (ctypes.c_char_p, [_i, _i]),
+    "lpc_phase_name": (ctypes.c_char_p, [_vp, _i]),
+    "lpc_engine_version": (_i, [_vp]),
     "lpc_plan_bytes": (_i, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
 }
 

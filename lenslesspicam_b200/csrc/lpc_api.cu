@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "lpc_admm.cuh"
+#include "lpc_fft_plan.h"
+#include "lpc_fused.cuh"
 #include "lpc_gd.cuh"
 #include "lpc_setup.cuh"
 #include "lpc_util.cuh"
@@ -74,6 +76,8 @@ struct lpc_plan_s {
     virtual int bytes_per_iter(double*) = 0;
     virtual int launches_per_iter(int*, int*) = 0;
     virtual int profile(int, cudaStream_t, double*, int*) = 0;
+    virtual const char* phase_name(int) = 0;
+    virtual int engine_version() = 0;
     virtual size_t plan_bytes() = 0;
 };
 
@@ -113,6 +117,20 @@ struct Plan : lpc_plan_s {
     T* rpad = nullptr;     // [Np][plane] C2R output
     T* mom = nullptr;      // [Np][h][w]  Nesterov p / FISTA xk_prev
     bool xpad_border_dirty = false;
+    // engine v2 (lpc_fused.cuh): own FFTs fused with the spatial / spectral updates
+    bool v2 = false;
+    Cplx* Tin = nullptr;    // T-layout row spectra of (V, HV)/Wp      [Np][NT][Hp][2][NCT]
+    Cplx* Tout = nullptr;   // T-layout row spectra of 2(a, xi')
+    Cplx* Ht = nullptr;     // H in tile layout [DC][NT][Hp][NCT]
+    T* Rt = nullptr;        // Rn/2 in tile layout
+    Cplx* tw_row = nullptr; // per-pass twiddle tables
+    Cplx* tw_col = nullptr;
+    Cplx* spec1 = nullptr;  // [Np][splane], warm start only (lazily allocated)
+    FftPlan plan_row{}, plan_col{};
+    FusedK fk{};
+    int ppt_row = 0, ppt_col = 0;
+    size_t smem_row = 0, smem_col = 0;
+    bool vh_valid = false;  // VH holds the V / HV of the current iterate
     // ---- cuFFT
     cufftHandle fwd_psf = 0, fwd = 0, inv = 0, fwd1 = 0, inv1 = 0;
     bool have_fwd_psf = false, have_fwd = false, have_inv = false, have_1 = false;
@@ -230,8 +248,11 @@ struct Plan : lpc_plan_s {
         if ((rc = alloc(&consts, (size_t)4 * C))) return rc;
         if ((rc = alloc(&data, (size_t)Np * h * dpitch))) return rc;  // sized for Dd == D
         int nb = Np;
+        if (algo == LPC_ALGO_ADMM && !(flags & LPC_FLAG_ENGINE_V1) && getenv("LPC_ENGINE_V1") == nullptr) {
+            if ((rc = init_v2())) return rc;
+        }
         if (algo == LPC_ALGO_ADMM) {
-            nb = 2 * Np;
+            nb = v2 ? 0 : 2 * Np;
             if ((rc = alloc(&VH, (size_t)2 * Np * plane))) return rc;
             if ((rc = alloc(&AX, (size_t)2 * Np * plane))) return rc;
             if ((rc = alloc(&rho, (size_t)Np * plane))) return rc;
@@ -247,16 +268,134 @@ struct Plan : lpc_plan_s {
                     if ((rc = alloc(&mom, (size_t)Np * h * w))) return rc;
             }
         }
-        if ((rc = alloc(&spec, (size_t)nb * splane))) return rc;
+        if (nb > 0 && (rc = alloc(&spec, (size_t)nb * splane))) return rc;
         if ((rc = make_fft(&fwd_psf, &have_fwd_psf, FftTraits<T>::R2C, DC))) return rc;
-        if ((rc = make_fft(&fwd, &have_fwd, FftTraits<T>::R2C, nb))) return rc;
-        if ((rc = make_fft(&inv, &have_inv, FftTraits<T>::C2R, nb))) return rc;
+        if (nb > 0) {
+            if ((rc = make_fft(&fwd, &have_fwd, FftTraits<T>::R2C, nb))) return rc;
+            if ((rc = make_fft(&inv, &have_inv, FftTraits<T>::C2R, nb))) return rc;
+        }
         if ((rc = bind_work())) return rc;
         // shift tables do not depend on the PSF
         k_shift_table<T><<<(Hp + 127) / 128, 128>>>(Sy, Hp, Hp);
         k_shift_table<T><<<(Nh + 127) / 128, 128>>>(Sx, Nh, Wp);
         LPC_KCHECK();
         LPC_CK(cudaDeviceSynchronize());
+        return LPC_OK;
+    }
+
+    // ---------------------------------------------------------------- engine v2 set-up
+    template <int MODE> int launch_rows(cudaStream_t st, const T* eta_i, T* eta_o, T sep_scale) {
+        const AdmmK<T> k = admm_k();
+        T* xi = AX + (int64_t)Np * plane;
+        const unsigned grid = (unsigned)(Np * fk.bands_per_plane);
+#define LPC_ROWS(P)                                                                                         \
+    k_admm_rows<T, P, MODE><<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, k, plan_row, tw_row, Tin, Tout, data, xi, \
+                                                                      rho, eta_i, eta_o, VH, sep_scale)
+        switch (ppt_row) {
+            case 4: LPC_ROWS(4); break;
+            default: LPC_ROWS(16); break;
+        }
+#undef LPC_ROWS
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+    int launch_cols(cudaStream_t st) {
+        dim3 grid(fk.NT, Np);
+#define LPC_COLS(P) \
+    k_admm_cols<T, P><<<grid, LPC_COLS_THREADS, smem_col, st>>>(fk, plan_col, tw_col, Tout, Tin, Ht, Rt, Sy, Sx)
+        switch (ppt_col) {
+            case 4: LPC_COLS(4); break;
+            default: LPC_COLS(17); break;
+        }
+#undef LPC_COLS
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+    template <typename K> int opt_in_smem(K kernel, size_t bytes) {
+        LPC_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        return LPC_OK;
+    }
+    template <int P> int opt_in_rows(size_t bytes) {
+        int rc;
+        if ((rc = opt_in_smem(k_admm_rows<T, P, LPC_ROWS_FULL>, bytes))) return rc;
+        if ((rc = opt_in_smem(k_admm_rows<T, P, LPC_ROWS_IFFT_ONLY>, bytes))) return rc;
+        return opt_in_smem(k_admm_rows<T, P, LPC_ROWS_FFT_ONLY>, bytes);
+    }
+
+    // decides whether the fused engine applies (5-smooth always holds; shared memory and the
+    // compiled points-per-thread bounds are the limits) and allocates its buffers
+    int init_v2() {
+        if (!make_fft_plan(Wp, &plan_row) || !make_fft_plan(Hp, &plan_col)) return LPC_OK;  // stay on v1
+        const int need_row = (Wp + LPC_ROWS_THREADS - 1) / LPC_ROWS_THREADS;
+        const int need_col = (2 * LPC_NCT * Hp + LPC_COLS_THREADS - 1) / LPC_COLS_THREADS;
+        ppt_row = need_row <= 4 ? 4 : need_row <= 16 ? 16 : 0;   // Wp <= 4096
+        ppt_col = need_col <= 4 ? 4 : need_col <= 17 ? 17 : 0;   // Hp <= 2176
+        if (!ppt_row || !ppt_col) return LPC_OK;
+        const int wlen = fft_padded_len(Wp, plan_row.padsh);
+        const int wp4 = (Wp + 3) & ~3;
+        smem_row = (size_t)((wlen + 1) & ~1) * sizeof(Cplx) + (size_t)5 * wp4 * sizeof(T);
+        smem_col = (size_t)fft_padded_len(2 * LPC_NCT * Hp, plan_col.padsh) * sizeof(Cplx);
+        int max_optin = 0;
+        LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
+        int rc;
+        switch (ppt_row) {
+            case 4: rc = opt_in_rows<4>(smem_row); break;
+            default: rc = opt_in_rows<16>(smem_row); break;
+        }
+        if (rc) return rc;
+        switch (ppt_col) {
+            case 4: rc = opt_in_smem(k_admm_cols<T, 4>, smem_col); break;
+            default: rc = opt_in_smem(k_admm_cols<T, 17>, smem_col); break;
+        }
+        if (rc) return rc;
+
+        fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;
+        fk.n_planes = Np; fk.DC = DC;
+        fk.padsh_row = plan_row.padsh; fk.padsh_col = plan_col.padsh;
+        // bands: about one wave of CTAs over the SMs (resident CTAs per SM from the occupancy API)
+        int sms = 148, occ = 1;
+        LPC_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        switch (ppt_row) {
+            case 4: LPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_rows<T, 4, LPC_ROWS_FULL>, LPC_ROWS_THREADS, smem_row)); break;
+            default: LPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_rows<T, 16, LPC_ROWS_FULL>, LPC_ROWS_THREADS, smem_row)); break;
+        }
+        if (occ < 1) return LPC_OK;
+        const char* env_rpb = getenv("LPC_ROWS_PER_BAND");
+        int target = sms * occ / Np;
+        if (target < 1) target = 1;
+        int rpb = (Hp + target - 1) / target;
+        if (rpb < 8) rpb = Hp < 8 ? Hp : 8;
+        if (env_rpb) rpb = atoi(env_rpb) > 0 ? atoi(env_rpb) : rpb;
+        fk.rows_per_band = rpb;
+        fk.bands_per_plane = (Hp + rpb - 1) / rpb;
+
+        const size_t tsz = (size_t)Np * fk.NT * Hp * 2 * LPC_NCT;
+        if ((rc = alloc(&Tin, tsz))) return rc;
+        if ((rc = alloc(&Tout, tsz))) return rc;
+        if ((rc = alloc(&Ht, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
+        if ((rc = alloc(&Rt, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
+        std::vector<Cplx> tw;
+        fill_fft_twiddles(plan_row, &tw);
+        if ((rc = alloc(&tw_row, tw.size()))) return rc;
+        LPC_CK(cudaMemcpy(tw_row, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+        fill_fft_twiddles(plan_col, &tw);
+        if ((rc = alloc(&tw_col, tw.size()))) return rc;
+        LPC_CK(cudaMemcpy(tw_col, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+        v2 = true;
+        return LPC_OK;
+    }
+    int tile_HR(cudaStream_t st) {
+        k_tile_HR<T><<<1184, 256, 0, st>>>(Hc, Rn, Ht, Rt, DC, Hp, Nh, fk.NT);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+    // V, HV of the current iterate -> VH (they are not stored by the fused engine)
+    int materialise_vh(cudaStream_t st) {
+        if (!v2 || vh_valid) return LPC_OK;
+        int rc = launch_rows<LPC_ROWS_IFFT_ONLY>(st, eta[eta_cur], eta[eta_cur ^ 1], T(1));
+        if (rc) return rc;
+        vh_valid = true;
         return LPC_OK;
     }
 
@@ -307,6 +446,7 @@ struct Plan : lpc_plan_s {
     int compute_R(cudaStream_t st) {
         k_admm_R<T><<<1184, 256, 0, st>>>(Hc, Rn, DC, Hp, Wp, Nh, mu1, mu2, mu3);
         LPC_KCHECK();
+        if (v2) return tile_HR(st);
         return LPC_OK;
     }
     int compute_alpha(cudaStream_t st) {
@@ -435,21 +575,34 @@ struct Plan : lpc_plan_s {
             LPC_CK(cudaMemsetAsync(rho, 0, (size_t)Np * plane * sizeof(T), st));
             LPC_CK(cudaMemsetAsync(eta[0], 0, (size_t)2 * Np * plane * sizeof(T), st));
             eta_cur = 0;
+            if (v2) {
+                LPC_CK(cudaMemsetAsync(Tin, 0, (size_t)Np * fk.NT * Hp * 2 * LPC_NCT * sizeof(Cplx), st));
+                vh_valid = true;  // V = HV = 0 sits in VH
+            }
+            Cplx* sp = spec;
             if (dev_init) {
                 if ((rc = ensure_single_plans())) return rc;
+                if (v2) {
+                    if (!spec1 && (rc = alloc(&spec1, (size_t)Np * splane))) return rc;
+                    sp = spec1;
+                }
                 // V = initial_est (padded shape, recon.py:296-299)
                 if ((rc = pack((const T*)dev_init, contiguous(D, Hp, Wp, C), nullptr, Strides5{}, VH, B, D, Hp, Wp, plane,
                                Wp, 0, 0, st))) return rc;
                 // HV = convolve(V) (admm.py:175)
                 LPC_CF(cufftSetStream(fwd1, st));
                 LPC_CF(cufftSetStream(inv1, st));
-                LPC_CF(FftTraits<T>::fwd(fwd1, VH, spec));
-                if ((rc = spec_mul(spec, Np, 0, st))) return rc;
-                LPC_CF(FftTraits<T>::inv(inv1, spec, VH + (int64_t)Np * plane));
+                LPC_CF(FftTraits<T>::fwd(fwd1, VH, sp));
+                if ((rc = spec_mul(sp, Np, 0, st))) return rc;
+                LPC_CF(FftTraits<T>::inv(inv1, sp, VH + (int64_t)Np * plane));
                 dim3 grid((Wp + 127) / 128, Hp, Np);
                 k_admm_warm_start<T><<<grid, 128, 0, st>>>(admm_k(), VH, VH + (int64_t)Np * plane, AX + (int64_t)Np * plane,
                                                           rho, eta[0]);
                 LPC_KCHECK();
+                if (v2) {  // row spectra of (V, HV)/Wp into Tin
+                    if ((rc = launch_rows<LPC_ROWS_FFT_ONLY>(st, eta[0], eta[1], (T)(0.5 / (double)Wp)))) return rc;
+                    vh_valid = true;
+                }
             }
         } else {
             // gd.py:94-126
@@ -474,6 +627,16 @@ struct Plan : lpc_plan_s {
     int admm_iteration(cudaStream_t st, cudaEvent_t* ev = nullptr) {
 #define LPC_EV(i) do { if (ev) LPC_CK(cudaEventRecord(ev[i], st)); } while (0)
         LPC_EV(0);
+        if (v2) {
+            int rc = launch_rows<LPC_ROWS_FULL>(st, eta[eta_cur], eta[eta_cur ^ 1], T(1));
+            if (rc) return rc;
+            eta_cur ^= 1;
+            vh_valid = false;
+            LPC_EV(1);
+            if ((rc = launch_cols(st))) return rc;
+            LPC_EV(2);
+            return LPC_OK;
+        }
         const AdmmK<T> k = admm_k();
         T* a = AX;
         T* xi = AX + (int64_t)Np * plane;
@@ -548,9 +711,9 @@ struct Plan : lpc_plan_s {
         if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "profile", "convolver plans do not iterate");
         if (!psf_set || !data_set || !state_ready) return fail(LPC_ESTATE, "profile", "PSF, data and reset first");
         LPC_CK(cudaSetDevice(device));
-        LPC_CF(cufftSetStream(fwd, st));
-        LPC_CF(cufftSetStream(inv, st));
-        const int np = (algo == LPC_ALGO_ADMM) ? 4 : 8;
+        if (have_fwd) LPC_CF(cufftSetStream(fwd, st));
+        if (have_inv) LPC_CF(cufftSetStream(inv, st));
+        const int np = (algo == LPC_ALGO_ADMM) ? (v2 ? 2 : 4) : 8;
         cudaEvent_t ev[9];
         for (int i = 0; i <= np; ++i) LPC_CK(cudaEventCreate(&ev[i]));
         for (int i = 0; i < np; ++i) ms[i] = 0.0;
@@ -584,8 +747,8 @@ struct Plan : lpc_plan_s {
         if (n_iter < 0) return fail(LPC_EINVAL, "run", "n_iter < 0");
         if (n_iter == 0) return LPC_OK;
         LPC_CK(cudaSetDevice(device));
-        LPC_CF(cufftSetStream(fwd, st));
-        LPC_CF(cufftSetStream(inv, st));
+        if (have_fwd) LPC_CF(cufftSetStream(fwd, st));
+        if (have_inv) LPC_CF(cufftSetStream(inv, st));
         static const bool env_no_graph = (getenv("LPC_NO_GRAPH") != nullptr);
         const bool use_graph = !(flags & LPC_FLAG_NO_GRAPH) && !env_no_graph && st != nullptr;
         if (!use_graph) return iterate(n_iter, st);
@@ -626,6 +789,7 @@ struct Plan : lpc_plan_s {
         if (!state_ready) return fail(LPC_ESTATE, "get_image", "no state: call lpc_reset");
         if (!dev_out) return fail(LPC_EINVAL, "get_image", "null output");
         LPC_CK(cudaSetDevice(device));
+        if (algo == LPC_ALGO_ADMM) { int rc = materialise_vh(st); if (rc) return rc; }
         const T* src = (algo == LPC_ALGO_ADMM) ? VH : xpad;
         return unpack(src, plane, Wp, sy, sx, (T*)dev_out, B * D, h, w, 1, st);
     }
@@ -643,6 +807,7 @@ struct Plan : lpc_plan_s {
         if (!dev_out) return fail(LPC_EINVAL, "get_state", "null output");
         LPC_CK(cudaSetDevice(device));
         if (algo == LPC_ALGO_ADMM) {
+            if (which == LPC_STATE_IMAGE_EST || which == LPC_STATE_FORWARD) { int rc = materialise_vh(st); if (rc) return rc; }
             const T* src = nullptr;
             switch (which) {
                 case LPC_STATE_IMAGE_EST: src = VH; break;
@@ -709,7 +874,7 @@ struct Plan : lpc_plan_s {
     }
     int launches_per_iter(int* total, int* own) override {
         int o = 0, f = 0;
-        if (algo == LPC_ALGO_ADMM) { o = 2; f = 2; }
+        if (algo == LPC_ALGO_ADMM) { o = 2; f = v2 ? 0 : 2; }
         else if (algo >= LPC_ALGO_GD) { o = 4; f = 4; }
         else { o = 3; f = 2; }
         if (own) *own = o;
@@ -717,6 +882,16 @@ struct Plan : lpc_plan_s {
         return LPC_OK;
     }
     size_t plan_bytes() override { return total_bytes + work_bytes; }
+    int engine_version() override { return v2 ? 2 : 1; }
+    const char* phase_name(int phase) override {
+        static const char* admm1[] = {"admm_spatial(K1)", "cufft_r2c", "admm_spectral(K2)", "cufft_c2r"};
+        static const char* admm2[] = {"admm_rows(B)", "admm_cols(A)"};
+        static const char* gd[] = {"cufft_r2c", "spec_mul_H", "cufft_c2r", "residual", "cufft_r2c", "spec_mul_Hadj", "cufft_c2r", "update"};
+        if (algo == LPC_ALGO_ADMM && v2 && phase >= 0 && phase < 2) return admm2[phase];
+        if (algo == LPC_ALGO_ADMM && !v2 && phase >= 0 && phase < 4) return admm1[phase];
+        if (algo >= LPC_ALGO_GD && phase >= 0 && phase < 8) return gd[phase];
+        return "";
+    }
 };
 
 }  // namespace
@@ -859,13 +1034,8 @@ int lpc_profile(lpc_plan_t plan, int n_iter, void* stream, double* phase_ms, int
     if (!phase_ms || !n_phases || n_iter < 1) return LPC_EINVAL;
     return plan->profile(n_iter, (cudaStream_t)stream, phase_ms, n_phases);
 }
-const char* lpc_phase_name(int algo, int phase) {
-    static const char* admm[] = {"admm_spatial(K1)", "cufft_r2c", "admm_spectral(K2)", "cufft_c2r"};
-    static const char* gd[] = {"cufft_r2c", "spec_mul_H", "cufft_c2r", "residual", "cufft_r2c", "spec_mul_Hadj", "cufft_c2r", "update"};
-    if (algo == LPC_ALGO_ADMM && phase >= 0 && phase < 4) return admm[phase];
-    if (algo >= LPC_ALGO_GD && algo <= LPC_ALGO_FISTA && phase >= 0 && phase < 8) return gd[phase];
-    return "";
-}
+const char* lpc_phase_name(lpc_plan_t plan, int phase) { return plan ? plan->phase_name(phase) : ""; }
+int lpc_engine_version(lpc_plan_t plan) { return plan ? plan->engine_version() : 0; }
 int lpc_plan_bytes(lpc_plan_t plan, size_t* bytes) {
     LPC_NEED(plan);
     if (!bytes) return LPC_EINVAL;

@@ -104,6 +104,8 @@ class ReconstructionAlgorithm(abc.ABC):
         self._plan = None     # plan of the current batch size
         self._B = 1
         self._flags = _lib.FLAG_NO_GRAPH if kwargs.get("no_graph", False) else _lib.FLAG_NONE
+        if kwargs.get("engine", None) == "v1":  # K1/K2 + cuFFT instead of the fused own-FFT engine (A/B, bisecting)
+            self._flags |= _lib.FLAG_ENGINE_V1
 
         if initial_est is not None:
             self._set_initial_estimate(initial_est)
@@ -158,7 +160,7 @@ class ReconstructionAlgorithm(abc.ABC):
     def _convolver(self):
         """RealFFTConvolve2D mirror (built on first use; the solver itself does not need it)."""
         if self._convolver_obj is None:
-            kw = {k: v for k, v in self._convolver_param.items() if k not in ("dtype", "pad", "no_graph")}
+            kw = {k: v for k, v in self._convolver_param.items() if k not in ("dtype", "pad", "no_graph", "engine")}
             self._convolver_obj = RealFFTConvolve2D(self._psf, dtype=self._dtype, pad=self._pad, **kw)
         return self._convolver_obj
 
@@ -372,7 +374,7 @@ class ReconstructionAlgorithm(abc.ABC):
             lensless = self._data
         if psfs is None:
             psfs = self._psf
-        kw = {k: v for k, v in self._convolver_param.items() if k != "no_graph"}
+        kw = {k: v for k, v in self._convolver_param.items() if k not in ("no_graph", "engine")}
         convolver = RealFFTConvolve2D(psfs.to(prediction.device), **kw)
         if not convolver.pad:
             prediction = convolver._pad(prediction)

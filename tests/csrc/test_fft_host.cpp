@@ -1,0 +1,126 @@
+// Host harness for lpc_fft.cuh: runs the SAME in-register DFTs, Stockham pass index math,
+// padding and twiddle tables on the CPU (threads emulated by loops, the CTA barrier by the
+// loop boundary between the load+compute phase and the store phase) and compares against a
+// naive O(N^2) DFT in long double.  Built and run by tests/test_fft_host.py (no GPU needed).
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "lpc_fft_plan.h"
+
+using namespace lpc;
+
+template <typename T, int DIR> static void naive(const std::vector<std::complex<long double>>& x, std::vector<std::complex<long double>>& X) {
+    const int N = (int)x.size();
+    X.assign(N, 0);
+    for (int k = 0; k < N; ++k) {
+        std::complex<long double> acc = 0;
+        for (int n = 0; n < N; ++n) {
+            long double ang = DIR * 2.0L * M_PIl * (long double)(((long long)n * k) % N) / N;
+            acc += x[n] * std::complex<long double>(cosl(ang), sinl(ang));
+        }
+        X[k] = acc;
+    }
+}
+
+template <typename T, int R, int DIR> static double test_dft() {
+    using C = typename CxT<T>::type;
+    C v[R];
+    std::vector<std::complex<long double>> x(R), X;
+    for (int i = 0; i < R; ++i) {
+        v[i].x = (T)(rand() / (double)RAND_MAX - 0.5);
+        v[i].y = (T)(rand() / (double)RAND_MAX - 0.5);
+        x[i] = {v[i].x, v[i].y};
+    }
+    naive<T, DIR>(x, X);
+    Dft<T, R, DIR>::run(v);
+    double err = 0;
+    for (int i = 0; i < R; ++i) err = fmax(err, (double)std::abs(std::complex<long double>(v[i].x, v[i].y) - X[i]));
+    return err;
+}
+
+template <typename T, int R, int DIR>
+static void emu_pass(std::vector<typename CxT<T>::type>& sm, const typename CxT<T>::type* tw, const FftPlan& plan, int Ns, int nbatch, int bs, int es) {
+    using C = typename CxT<T>::type;
+    const int nb = plan.N / R, total = nb * nbatch;
+    std::vector<C> regs((size_t)total * R);
+    for (int g = 0; g < total; ++g) {  // "threads": load + compute phase
+        int b, j;
+        if (es > 1) { b = g % nbatch; j = g / nbatch; } else { b = g / nb; j = g - b * nb; }
+        fft_bfly_load<T, R>(sm.data(), b * bs, es, plan.padsh, plan.N, j, &regs[(size_t)g * R]);
+        fft_bfly_compute<T, R, DIR>(&regs[(size_t)g * R], tw, Ns, j);
+    }
+    for (int g = 0; g < total; ++g) {  // barrier, then store phase
+        int b, j;
+        if (es > 1) { b = g % nbatch; j = g / nbatch; } else { b = g / nb; j = g - b * nb; }
+        fft_bfly_store<T, R>(sm.data(), b * bs, es, plan.padsh, Ns, j, &regs[(size_t)g * R]);
+    }
+}
+
+template <typename T, int DIR>
+static void emu_fft(std::vector<typename CxT<T>::type>& sm, const FftPlan& plan, const std::vector<typename CxT<T>::type>& tw, int nbatch, int bs, int es) {
+    for (int p = 0; p < plan.npass; ++p) {
+        const auto* t = tw.data() + plan.tw_off[p];
+        switch (plan.radix[p]) {
+#define CASE(R) case R: emu_pass<T, R, DIR>(sm, t, plan, plan.Ns[p], nbatch, bs, es); break;
+            CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(9) CASE(10) CASE(12) CASE(15) CASE(16)
+#undef CASE
+            default: printf("bad radix %d\n", plan.radix[p]); exit(2);
+        }
+    }
+}
+
+template <typename T, int DIR> static double test_fft(int N, int nbatch, bool interleaved) {
+    using C = typename CxT<T>::type;
+    FftPlan plan;
+    if (!make_fft_plan(N, &plan)) { printf("no plan for %d\n", N); exit(2); }
+    std::vector<C> tw;
+    fill_fft_twiddles(plan, &tw);
+    const int es = interleaved ? nbatch : 1;
+    const int bs = interleaved ? 1 : N;  // batch stride in LOGICAL elements (padding applies to the sum)
+    std::vector<C> sm(fft_padded_len(N * nbatch, plan.padsh) + 8);
+    std::vector<std::vector<std::complex<long double>>> x(nbatch, std::vector<std::complex<long double>>(N));
+    for (int b = 0; b < nbatch; ++b)
+        for (int i = 0; i < N; ++i) {
+            C c; c.x = (T)(rand() / (double)RAND_MAX - 0.5); c.y = (T)(rand() / (double)RAND_MAX - 0.5);
+            sm[fft_pad(b * bs + i * es, plan.padsh)] = c;
+            x[b][i] = {c.x, c.y};
+        }
+    emu_fft<T, DIR>(sm, plan, tw, nbatch, bs, es);
+    double err = 0, mx = 0;
+    for (int b = 0; b < nbatch; ++b) {
+        std::vector<std::complex<long double>> X;
+        naive<T, DIR>(x[b], X);
+        for (int i = 0; i < N; ++i) {
+            C c = sm[fft_pad(b * bs + i * es, plan.padsh)];
+            err = fmax(err, (double)std::abs(std::complex<long double>(c.x, c.y) - X[i]));
+            mx = fmax(mx, (double)std::abs(X[i]));
+        }
+    }
+    printf("N=%5d batch=%d %s dir=%+d radices:", N, nbatch, interleaved ? "interleaved" : "planar     ", DIR);
+    for (int p = 0; p < plan.npass; ++p) printf(" %d", plan.radix[p]);
+    printf("  padsh=%d tw=%d  rel err %.2e\n", plan.padsh, plan.tw_len, err / mx);
+    return err / mx;
+}
+
+int main() {
+    int bad = 0;
+    double e;
+#define TD(R) \
+    e = test_dft<double, R, -1>(); if (e > 1e-14) { printf("dft<double,%d,fwd> err %.2e\n", R, e); bad++; } \
+    e = test_dft<double, R, +1>(); if (e > 1e-14) { printf("dft<double,%d,inv> err %.2e\n", R, e); bad++; } \
+    e = test_dft<float, R, -1>(); if (e > 5e-6) { printf("dft<float,%d,fwd> err %.2e\n", R, e); bad++; }
+    TD(2) TD(3) TD(4) TD(5) TD(6) TD(8) TD(9) TD(10) TD(12) TD(15) TD(16)
+    printf("in-register DFTs: %s\n", bad ? "FAILED" : "ok");
+    const int sizes[] = {2, 3, 4, 5, 6, 8, 9, 16, 27, 40, 45, 48, 54, 60, 64, 75, 96, 125, 270, 405, 480, 768, 1024, 2160, 3840};
+    for (int N : sizes) {
+        if (test_fft<double, -1>(N, 1, false) > 1e-13) bad++;
+        if (test_fft<double, +1>(N, 2, false) > 1e-13) bad++;
+        if (test_fft<float, -1>(N, 4, true) > 2e-6) bad++;
+        if (test_fft<float, +1>(N, 3, true) > 2e-6) bad++;
+    }
+    printf(bad ? "FAILED (%d)\n" : "ALL OK\n", bad);
+    return bad ? 1 : 0;
+}

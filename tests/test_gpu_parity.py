@@ -185,6 +185,39 @@ def test_batch_matches_per_sample_and_unrolled():
         assert rel_to_max(one.cpu().numpy(), out[b]) <= 1e-6
 
 
+# ------------------------------------------------------------------------------ engine v2 (fused own-FFT) vs v1 (cuFFT)
+def _engine_version(rec):
+    from lenslesspicam_b200 import _lib
+
+    return _lib.load().lpc_engine_version(rec._plan)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_engine_is_default_and_agrees_with_cufft_engine(case):
+    """ADMM runs the fused two-kernel engine (own FFTs) by default; engine="v1" (K1/K2 + cuFFT) is kept
+    for bisecting.  Both must agree to FFT round-off, state by state after one iteration."""
+    g = load_golden(case)
+    a, ra = run("admm", g["psf"], g["data"], 1)
+    b, rb = run("admm", g["psf"], g["data"], 1, engine="v1")
+    assert _engine_version(ra) == 2 and _engine_version(rb) == 1
+    from lenslesspicam_b200 import _lib
+
+    lib = _lib.load()
+    D, Hp, Wp, C = ra._padded_shape
+    for which, name in ((0, "V"), (1, "HV"), (2, "xi'"), (3, "rho'"), (4, "eta'0"), (5, "eta'1")):
+        outs = []
+        for r in (ra, rb):
+            o = torch.empty((1, D, Hp, Wp, C), device="cuda")
+            with r._stream as st:
+                _lib.check(lib.lpc_get_state(r._plan, which, o.data_ptr(), st), r._plan)
+            outs.append(o.cpu().numpy())
+        assert rel_to_max(outs[0], outs[1]) <= 2e-6, (case, name, rel_to_max(outs[0], outs[1]))
+    for n in (5, 30):
+        a, _ = run("admm", g["psf"], g["data"], n)
+        b, _ = run("admm", g["psf"], g["data"], n, engine="v1")
+        assert rel_to_max(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6, (case, n)
+
+
 # ------------------------------------------------------------------------------ live oracle parity
 @pytest.mark.parametrize("shape", [(135, 240, 3), (203, 61, 3), (100, 136, 1)])
 def test_parity_with_oracle_mid_size(shape):
