@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "lpc_admm.cuh"
@@ -51,6 +52,34 @@ template <> struct FftTraits<double> {
     static cufftResult inv(cufftHandle p, double2* in, double* out) { return cufftExecZ2D(p, (cufftDoubleComplex*)in, out); }
 };
 
+}  // namespace
+
+// ---- compiled menu of the fused engine (float only): padded size -> kernel instantiation
+namespace {
+using RowsKern = void (*)(FusedK, AdmmK<float>, const float2*, const float2*, float2*, const float*, float*, float*,
+                          const float*, float*, float*, float);
+using ColsKern = void (*)(FusedK, const float2*, const float2*, float2*, const float2*, const float*, const float2*,
+                          const float2*);
+struct RowsEntry { int N, npass, radix[4]; RowsKern kern[3]; };
+struct ColsEntry { int N, npass, radix[4]; ColsKern kern; };
+template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
+#define LPC_X(N, ...)                                                                                         \
+    {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__},                                                              \
+     {k_admm_rows<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_FULL>, k_admm_rows<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_IFFT_ONLY>, \
+      k_admm_rows<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_FFT_ONLY>}},
+const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
+#undef LPC_X
+#define LPC_X(N, ...) {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_admm_cols<float, FftSeq<N, __VA_ARGS__>>},
+const ColsEntry g_cols_menu[] = {LPC_COL_MENU(LPC_X)};
+#undef LPC_X
+const RowsEntry* find_rows(int N) {
+    for (const RowsEntry& e : g_rows_menu) if (e.N == N) return &e;
+    return nullptr;
+}
+const ColsEntry* find_cols(int N) {
+    for (const ColsEntry& e : g_cols_menu) if (e.N == N) return &e;
+    return nullptr;
+}
 }  // namespace
 
 // ------------------------------------------------------------------------------------
@@ -128,7 +157,6 @@ struct Plan : lpc_plan_s {
     Cplx* spec1 = nullptr;  // [Np][splane], warm start only (lazily allocated)
     FftPlan plan_row{}, plan_col{};
     FusedK fk{};
-    int ppt_row = 0, ppt_col = 0;
     size_t smem_row = 0, smem_col = 0;
     bool vh_valid = false;  // VH holds the V / HV of the current iterate
     // ---- cuFFT
@@ -284,106 +312,83 @@ struct Plan : lpc_plan_s {
     }
 
     // ---------------------------------------------------------------- engine v2 set-up
+    const RowsEntry* rows_entry = nullptr;
+    const ColsEntry* cols_entry = nullptr;
+
     template <int MODE> int launch_rows(cudaStream_t st, const T* eta_i, T* eta_o, T sep_scale) {
-        const AdmmK<T> k = admm_k();
-        T* xi = AX + (int64_t)Np * plane;
-        const unsigned grid = (unsigned)(Np * fk.bands_per_plane);
-#define LPC_ROWS(P)                                                                                         \
-    k_admm_rows<T, P, MODE><<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, k, plan_row, tw_row, Tin, Tout, data, xi, \
-                                                                      rho, eta_i, eta_o, VH, sep_scale)
-        switch (ppt_row) {
-            case 4: LPC_ROWS(4); break;
-            default: LPC_ROWS(16); break;
+        if constexpr (std::is_same<T, float>::value) {
+            const AdmmK<T> k = admm_k();
+            T* xi = AX + (int64_t)Np * plane;
+            const unsigned grid = (unsigned)(Np * fk.bands_per_plane);
+            rows_entry->kern[MODE]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, k, tw_row, Tin, Tout, data, xi, rho, eta_i,
+                                                                             eta_o, VH, sep_scale);
+            LPC_KCHECK();
         }
-#undef LPC_ROWS
-        LPC_KCHECK();
         return LPC_OK;
     }
     int launch_cols(cudaStream_t st) {
-        dim3 grid(fk.NT, Np);
-#define LPC_COLS(P) \
-    k_admm_cols<T, P><<<grid, LPC_COLS_THREADS, smem_col, st>>>(fk, plan_col, tw_col, Tout, Tin, Ht, Rt, Sy, Sx)
-        switch (ppt_col) {
-            case 4: LPC_COLS(4); break;
-            default: LPC_COLS(17); break;
+        if constexpr (std::is_same<T, float>::value) {
+            dim3 grid(fk.NT, Np);
+            cols_entry->kern<<<grid, LPC_COLS_THREADS, smem_col, st>>>(fk, tw_col, Tout, Tin, Ht, Rt, Sy, Sx);
+            LPC_KCHECK();
         }
-#undef LPC_COLS
-        LPC_KCHECK();
         return LPC_OK;
-    }
-    template <typename K> int opt_in_smem(K kernel, size_t bytes) {
-        LPC_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        return LPC_OK;
-    }
-    template <int P> int opt_in_rows(size_t bytes) {
-        int rc;
-        if ((rc = opt_in_smem(k_admm_rows<T, P, LPC_ROWS_FULL>, bytes))) return rc;
-        if ((rc = opt_in_smem(k_admm_rows<T, P, LPC_ROWS_IFFT_ONLY>, bytes))) return rc;
-        return opt_in_smem(k_admm_rows<T, P, LPC_ROWS_FFT_ONLY>, bytes);
     }
 
-    // decides whether the fused engine applies (5-smooth always holds; shared memory and the
-    // compiled points-per-thread bounds are the limits) and allocates its buffers
+    // decides whether the fused engine applies (float, both padded sizes in the compiled menu, shared
+    // memory fits) and allocates its buffers; otherwise the plan stays on engine v1
     int init_v2() {
-        if (!make_fft_plan(Wp, &plan_row) || !make_fft_plan(Hp, &plan_col)) return LPC_OK;  // stay on v1
-        const int need_row = (Wp + LPC_ROWS_THREADS - 1) / LPC_ROWS_THREADS;
-        const int need_col = (2 * LPC_NCT * Hp + LPC_COLS_THREADS - 1) / LPC_COLS_THREADS;
-        ppt_row = need_row <= 4 ? 4 : need_row <= 16 ? 16 : 0;   // Wp <= 4096
-        ppt_col = need_col <= 4 ? 4 : need_col <= 17 ? 17 : 0;   // Hp <= 2176
-        if (!ppt_row || !ppt_col) return LPC_OK;
-        const int wlen = fft_padded_len(Wp, plan_row.padsh);
-        const int wp4 = (Wp + 3) & ~3;
-        smem_row = (size_t)((wlen + 1) & ~1) * sizeof(Cplx) + (size_t)5 * wp4 * sizeof(T);
-        smem_col = (size_t)fft_padded_len(2 * LPC_NCT * Hp, plan_col.padsh) * sizeof(Cplx);
-        int max_optin = 0;
-        LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
-        int rc;
-        switch (ppt_row) {
-            case 4: rc = opt_in_rows<4>(smem_row); break;
-            default: rc = opt_in_rows<16>(smem_row); break;
-        }
-        if (rc) return rc;
-        switch (ppt_col) {
-            case 4: rc = opt_in_smem(k_admm_cols<T, 4>, smem_col); break;
-            default: rc = opt_in_smem(k_admm_cols<T, 17>, smem_col); break;
-        }
-        if (rc) return rc;
+        if constexpr (!std::is_same<T, float>::value) {
+            return LPC_OK;
+        } else {
+            rows_entry = find_rows(Wp);
+            cols_entry = find_cols(Hp);
+            if (!rows_entry || !cols_entry) return LPC_OK;
+            if (!make_fft_plan_from(Wp, rows_entry->radix, rows_entry->npass, &plan_row)) return LPC_OK;
+            if (!make_fft_plan_from(Hp, cols_entry->radix, cols_entry->npass, &plan_col)) return LPC_OK;
+            const int wlen = fft_padded_len(Wp, plan_row.padsh);
+            const int wp4 = (Wp + 3) & ~3;
+            smem_row = (size_t)((wlen + 1) & ~1) * sizeof(Cplx) + (size_t)5 * wp4 * sizeof(T);
+            smem_col = (size_t)fft_padded_len(2 * LPC_NCT * Hp, plan_col.padsh) * sizeof(Cplx);
+            int max_optin = 0;
+            LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+            if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
+            for (int m = 0; m < 3; ++m)
+                LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
 
-        fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;
-        fk.n_planes = Np; fk.DC = DC;
-        fk.padsh_row = plan_row.padsh; fk.padsh_col = plan_col.padsh;
-        // bands: about one wave of CTAs over the SMs (resident CTAs per SM from the occupancy API)
-        int sms = 148, occ = 1;
-        LPC_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        switch (ppt_row) {
-            case 4: LPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_rows<T, 4, LPC_ROWS_FULL>, LPC_ROWS_THREADS, smem_row)); break;
-            default: LPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_admm_rows<T, 16, LPC_ROWS_FULL>, LPC_ROWS_THREADS, smem_row)); break;
-        }
-        if (occ < 1) return LPC_OK;
-        const char* env_rpb = getenv("LPC_ROWS_PER_BAND");
-        int target = sms * occ / Np;
-        if (target < 1) target = 1;
-        int rpb = (Hp + target - 1) / target;
-        if (rpb < 8) rpb = Hp < 8 ? Hp : 8;
-        if (env_rpb) rpb = atoi(env_rpb) > 0 ? atoi(env_rpb) : rpb;
-        fk.rows_per_band = rpb;
-        fk.bands_per_plane = (Hp + rpb - 1) / rpb;
+            fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;
+            fk.n_planes = Np; fk.DC = DC;
+            // bands: about one wave of CTAs over the SMs (resident CTAs per SM from the occupancy API)
+            int sms = 148, occ = 1;
+            LPC_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            LPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rows_entry->kern[LPC_ROWS_FULL], LPC_ROWS_THREADS, smem_row));
+            if (occ < 1) return LPC_OK;
+            const char* env_rpb = getenv("LPC_ROWS_PER_BAND");
+            int target = sms * occ / Np;
+            if (target < 1) target = 1;
+            int rpb = (Hp + target - 1) / target;
+            if (rpb < 8) rpb = Hp < 8 ? Hp : 8;
+            if (env_rpb) rpb = atoi(env_rpb) > 0 ? atoi(env_rpb) : rpb;
+            fk.rows_per_band = rpb;
+            fk.bands_per_plane = (Hp + rpb - 1) / rpb;
 
-        const size_t tsz = (size_t)Np * fk.NT * Hp * 2 * LPC_NCT;
-        if ((rc = alloc(&Tin, tsz))) return rc;
-        if ((rc = alloc(&Tout, tsz))) return rc;
-        if ((rc = alloc(&Ht, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
-        if ((rc = alloc(&Rt, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
-        std::vector<Cplx> tw;
-        fill_fft_twiddles(plan_row, &tw);
-        if ((rc = alloc(&tw_row, tw.size()))) return rc;
-        LPC_CK(cudaMemcpy(tw_row, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
-        fill_fft_twiddles(plan_col, &tw);
-        if ((rc = alloc(&tw_col, tw.size()))) return rc;
-        LPC_CK(cudaMemcpy(tw_col, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
-        v2 = true;
-        return LPC_OK;
+            int rc;
+            const size_t tsz = (size_t)Np * fk.NT * Hp * 2 * LPC_NCT;
+            if ((rc = alloc(&Tin, tsz))) return rc;
+            if ((rc = alloc(&Tout, tsz))) return rc;
+            if ((rc = alloc(&Ht, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
+            if ((rc = alloc(&Rt, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
+            std::vector<Cplx> tw;
+            fill_fft_twiddles(plan_row, &tw);
+            if ((rc = alloc(&tw_row, tw.size()))) return rc;
+            LPC_CK(cudaMemcpy(tw_row, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            fill_fft_twiddles(plan_col, &tw);
+            if ((rc = alloc(&tw_col, tw.size()))) return rc;
+            LPC_CK(cudaMemcpy(tw_col, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            v2 = true;
+            return LPC_OK;
+        }
     }
     int tile_HR(cudaStream_t st) {
         k_tile_HR<T><<<1184, 256, 0, st>>>(Hc, Rn, Ht, Rt, DC, Hp, Nh, fk.NT);
@@ -426,6 +431,8 @@ struct Plan : lpc_plan_s {
         AdmmK<T> k;
         k.mu1 = (T)mu1; k.mu2 = (T)mu2; k.mu3 = (T)mu3;
         k.thr = (T)(tau / mu2);
+        k.inv_mu2 = T(1) / (T)mu2;
+        k.inv_mu3 = T(1) / (T)mu3;
         // X_divmat = 1/(pad(ones) + mu1) in the working precision (admm.py:193)
         k.xdiv_in = T(1) / (T(1) + (T)mu1);
         k.xdiv_out = T(1) / (T(0) + (T)mu1);
@@ -780,6 +787,7 @@ struct Plan : lpc_plan_s {
             }
         }
         LPC_CK(cudaGraphLaunch(gexec, st));
+        vh_valid = false;  // V / HV in VH are stale as soon as an iteration has run (engine v2 keeps only spectra)
         return LPC_OK;
     }
 

@@ -54,12 +54,34 @@ inline bool make_fft_plan(int N, FftPlan* plan, int max_radix = 16) {
     return true;
 }
 
+// plan from an explicit radix sequence (the compile-time FftSeq menus of lpc_fused.cuh)
+inline bool make_fft_plan_from(int N, const int* radices, int npass, FftPlan* plan) {
+    if (npass < 1 || npass > LPC_FFT_MAX_PASSES) return false;
+    long long prod = 1;
+    for (int p = 0; p < npass; ++p) prod *= radices[p];
+    if (prod != N) return false;
+    plan->N = N;
+    plan->npass = npass;
+    plan->padsh = (radices[0] & 1) ? 30 : 4;
+    int Ns = 1, off = 0;
+    for (int p = 0; p < npass; ++p) {
+        plan->radix[p] = radices[p];
+        plan->Ns[p] = Ns;
+        plan->tw_off[p] = off;
+        off += (Ns == 1) ? 0 : Ns * (radices[p] - 1);
+        Ns *= radices[p];
+    }
+    plan->tw_len = off > 0 ? off : 1;
+    return true;
+}
+
 // forward-sign tables: pass p, entry [(m-1)*Ns + k] = exp(-2*pi*i*m*k/(Ns*R)); computed in double
 template <typename C>
 inline void fill_fft_twiddles(const FftPlan& plan, std::vector<C>* out) {
     out->assign(plan.tw_len, C{});
-    for (int p = 1; p < plan.npass; ++p) {
+    for (int p = 0; p < plan.npass; ++p) {
         const int R = plan.radix[p], Ns = plan.Ns[p];
+        if (Ns == 1) continue;
         for (int m = 1; m < R; ++m)
             for (int k = 0; k < Ns; ++k) {
                 const long long num = ((long long)m * k) % ((long long)Ns * R);

@@ -8,9 +8,9 @@
 //   duals  xi', rho', eta' (spatial, planar)                                     4P
 //   Tin    row spectra of (V, HV)/Wp  after A's column IFFT                       2Sp
 //   Tout   row spectra of 2*(a, xi')  after B's row FFT                           2Sp
-// so one iteration moves  B: 2Sp + 4P + P(eta'0 halo, L2) + d in, 4P + 2Sp out;  A: 2Sp + H + R in,
-// 2Sp out  =  8P + 9.5Sp + d  ~ 1.77 GB at 3x1080x1920 (v1 with cuFFT: ~3.3 GB; SURVEY's
-// canonical figure 16P + 9.5Sp + d = 2.56 GB counts a, V, HV materialised).
+// so one iteration moves  B: 2Sp + 4P (+ the eta'0 halo row, L2) + d in, 4P + 2Sp out;
+// A: 2Sp + H + R in, 2Sp out  =  8P + 9.5Sp + d  ~ 1.77 GB at 3x1080x1920 (v1 with cuFFT: ~3.3 GB;
+// SURVEY's canonical figure 16P + 9.5Sp + d = 2.56 GB counts a, V, HV materialised).
 //
 // Two real rows per complex transform: B packs z = a + i*xi' (forward) and Y = Vhat + i*HVhat
 // (inverse) so every row transform is ONE complex FFT of length Wp (any parity of Wp), with
@@ -23,6 +23,9 @@
 // A reads/writes one tile (all ky of NCT columns, both slots) as ONE contiguous 2*NCT*Hp*8-byte
 // block; B touches a 2*NCT*8 = 32-byte chunk per (tile, row).
 //
+// The transforms use compile-time radix sequences (FftSeq, lpc_fft.cuh): the kernels are
+// instantiated for the menu of padded sizes below; any other size runs engine v1 (K1/K2 + cuFFT).
+//
 // Reference semantics reproduced: admm.py:232-329 (see lpc_admm.cuh for the per-pixel algebra,
 // which is shared), rfft_convolve.py:133-223 (H, conj(H), ifftshift as the phase S).
 #pragma once
@@ -32,44 +35,120 @@
 
 namespace lpc {
 
-constexpr int LPC_NCT = 2;           // columns per tile and slot
+constexpr int LPC_NCT = 2;  // columns per tile and slot
 constexpr int LPC_ROWS_THREADS = 256;
-constexpr int LPC_COLS_THREADS = 512;
+constexpr int LPC_COLS_THREADS = 1024;
+
+// padded sizes with a compiled fast path: X(N, radices...).  Rows = Wp, columns = Hp.
+// 3840x2160: 1080x1920 (headline); 2048x1536 / 1024x768 / 512x384: the bundled 3040x4056 data at
+// downsample 4 / 8 / 16; the small ones are the shapes of tests/golden (odd, mixed, gray).
+#define LPC_ROW_MENU(X) \
+    X(3840, 15, 16, 16) X(2048, 16, 16, 8) X(1024, 16, 16, 4) X(512, 16, 8, 4) X(480, 15, 16, 2) \
+    X(288, 9, 16, 2) X(125, 5, 5, 5) X(75, 15, 5) X(64, 16, 4) X(54, 9, 6)
+#define LPC_COL_MENU(X) \
+    X(2160, 15, 16, 9) X(1536, 12, 16, 8) X(768, 3, 16, 16) X(384, 3, 16, 8) X(405, 15, 9, 3) \
+    X(270, 15, 9, 2) X(200, 5, 8, 5) X(48, 3, 16) X(45, 15, 3) X(40, 5, 8) X(27, 9, 3)
 
 struct FusedK {
-    int Hp, Wp, Nh, NT;      // NT tiles of LPC_NCT columns cover Nh = Wp/2+1
+    int Hp, Wp, Nh, NT;  // NT tiles of LPC_NCT columns cover Nh = Wp/2+1
     int n_planes, DC;
     int rows_per_band, bands_per_plane;
-    int padsh_row, padsh_col;
 };
 
 enum { LPC_ROWS_FULL = 0, LPC_ROWS_IFFT_ONLY = 1, LPC_ROWS_FFT_ONLY = 2 };
 
+// ---- B helper: gather one row of Tin into W as the full-length complex row Y = Vhat + i*HVhat
+//      (Hermitian extension for kx > Wp/2), inverse FFT, scatter to the real rows
+template <typename T, typename SEQ>
+__device__ __forceinline__ void rows_gather_ifft(const typename CxT<T>::type* __restrict__ TinP, int64_t tile_stride,
+                                                 int row, int NT, typename CxT<T>::type* W,
+                                                 const typename CxT<T>::type* __restrict__ tw, T* Vdst, T* HVdst, int tid) {
+    using C = typename CxT<T>::type;
+    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
+    for (int t = tid; t < NT; t += NTH) {
+        const C* src = TinP + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
+        C vh[NCT], hh[NCT];
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) { vh[c] = src[c]; hh[c] = src[NCT + c]; }
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            const int kx = t * NCT + c;
+            if (kx < Nh) {
+                C y; y.x = vh[c].x - hh[c].y; y.y = vh[c].y + hh[c].x;
+                W[fft_pad(kx, PADSH)] = y;
+                const int m = Wp - kx;
+                if (kx >= 1 && m >= Nh) {
+                    C ym; ym.x = vh[c].x + hh[c].y; ym.y = hh[c].x - vh[c].y;
+                    W[fft_pad(m, PADSH)] = ym;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    CtaFftStatic<T, SEQ, +1, 1, NTH>::run(W, tw, tid);
+    for (int j = tid; j < Wp; j += NTH) {
+        const C c = W[fft_pad(j, PADSH)];
+        Vdst[j] = c.x;
+        if (HVdst) HVdst[j] = c.y;
+    }
+    __syncthreads();
+}
+
+// ---- B helper: forward FFT of the row held in W (z = a + i*xi'), separate the two real spectra
+//      and store the half spectrum to row `row` of Tdst (T-layout)
+template <typename T, typename SEQ>
+__device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const typename CxT<T>::type* __restrict__ tw,
+                                               typename CxT<T>::type* __restrict__ Tdst, int64_t tile_stride, int row,
+                                               int NT, T sep_scale, int tid) {
+    using C = typename CxT<T>::type;
+    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
+    CtaFftStatic<T, SEQ, -1, 1, NTH>::run(W, tw, tid);
+    for (int t = tid; t < NT; t += NTH) {
+        C a[NCT], x[NCT];
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            const int kx = t * NCT + c;
+            a[c].x = a[c].y = x[c].x = x[c].y = T(0);
+            if (kx < Nh) {
+                const C zk = W[fft_pad(kx, PADSH)];
+                const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PADSH)];
+                a[c].x = (zk.x + zm.x) * sep_scale;  // Z[k] + conj(Z[-k])
+                a[c].y = (zk.y - zm.y) * sep_scale;
+                x[c].x = (zk.y + zm.y) * sep_scale;  // (Z[k] - conj(Z[-k])) / i
+                x[c].y = (zm.x - zk.x) * sep_scale;
+            }
+        }
+        C* dst = Tdst + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) { dst[c] = a[c]; dst[NCT + c] = x[c]; }
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
 // B: one CTA marches down a band of rows of one plane.
-// shared memory:  W  complex[padded Wp]  (row transform, in place)
-//                 Vr real[3][Wp]         rolling window of V rows i-1, i, i+1
-//                 HVr real[2][Wp]        HV rows i, i+1
+// shared memory:  W   complex[padded Wp]   row transform, in place
+//                 Vr  real[3][Wp]          rolling window of V rows i-1, i, i+1
+//                 HVr real[2][Wp]          HV rows i, i+1
 // MODE FULL      : the ADMM row step.
 // MODE IFFT_ONLY : only materialise V, HV (planar spatial, VH[2][planes][Hp][Wp]) -- _form_image / debug.
 // MODE FFT_ONLY  : only transform given V, HV into Tin (warm start, admm.py:154-155,172-176).
 // ---------------------------------------------------------------------------------------------
-template <typename T, int PPT, int MODE>
+template <typename T, typename SEQ, int MODE>
 __global__ void __launch_bounds__(LPC_ROWS_THREADS, 2)
-k_admm_rows(FusedK f, AdmmK<T> k, FftPlan plan, const typename CxT<T>::type* __restrict__ tw,
+k_admm_rows(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict__ tw,
             const typename CxT<T>::type* __restrict__ Tin, typename CxT<T>::type* __restrict__ Tout,
             const T* __restrict__ data, T* __restrict__ xi, T* __restrict__ rho, const T* __restrict__ eta_in,
             T* __restrict__ eta_out, T* __restrict__ VH, T sep_scale) {
     using C = typename CxT<T>::type;
-    constexpr int NTH = LPC_ROWS_THREADS;
-    constexpr int NCT = LPC_NCT;
+    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT;
+    constexpr int Wp = SEQ::N, PADSH = SEQ::padsh;
+    constexpr int wlen = Wp + (Wp >> PADSH) + 1;
+    constexpr int wp4 = (Wp + 3) & ~3;  // keep the real rows 16-byte aligned
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int Wp = f.Wp, Hp = f.Hp, Nh = f.Nh, NT = f.NT;
-    const int padsh = plan.padsh;
-    const int wlen = fft_padded_len(Wp, padsh);
+    const int Hp = f.Hp, NT = f.NT;
     C* W = reinterpret_cast<C*>(smem_raw);
-    const int wp4 = (Wp + 3) & ~3;  // keep the real rows 16-byte aligned
     T* Vr = reinterpret_cast<T*>(W + ((wlen + 1) & ~1));
     T* HVr = Vr + 3 * wp4;
 
@@ -85,67 +164,9 @@ k_admm_rows(FusedK f, AdmmK<T> k, FftPlan plan, const typename CxT<T>::type* __r
     const C* TinP = Tin + (int64_t)p * NT * tile_stride;
     C* ToutP = Tout + (int64_t)p * NT * tile_stride;
 
-    // ---- gather one row of Tin into W as the full-length complex row  Y = Vhat + i*HVhat
-    //      (Hermitian extension for kx > Wp/2), inverse FFT, scatter to the real rows
-    auto load_ifft_row = [&](int row, T* Vdst, T* HVdst) {
-        for (int t = tid; t < NT; t += NTH) {
-            const C* src = TinP + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
-            C vh[NCT], hh[NCT];
-#pragma unroll
-            for (int c = 0; c < NCT; ++c) { vh[c] = src[c]; hh[c] = src[NCT + c]; }
-#pragma unroll
-            for (int c = 0; c < NCT; ++c) {
-                const int kx = t * NCT + c;
-                if (kx < Nh) {
-                    C y; y.x = vh[c].x - hh[c].y; y.y = vh[c].y + hh[c].x;
-                    W[fft_pad(kx, padsh)] = y;
-                    const int m = Wp - kx;
-                    if (kx >= 1 && m >= Nh) {
-                        C ym; ym.x = vh[c].x + hh[c].y; ym.y = hh[c].x - vh[c].y;
-                        W[fft_pad(m, padsh)] = ym;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        cta_fft<T, +1, PPT>(W, plan, tw, 1, 0, 1, tid, NTH);
-        for (int j = tid; j < Wp; j += NTH) {
-            const C c = W[fft_pad(j, padsh)];
-            Vdst[j] = c.x;
-            if (HVdst) HVdst[j] = c.y;
-        }
-        __syncthreads();
-    };
-
-    // ---- forward FFT of the row held in W (z = a + i*xi'), separate the two real spectra and
-    //      store the half spectrum to row `row` of Tdst (T-layout)
-    auto fft_store_row = [&](int row, C* Tdst) {
-        cta_fft<T, -1, PPT>(W, plan, tw, 1, 0, 1, tid, NTH);
-        for (int t = tid; t < NT; t += NTH) {
-            C a[NCT], x[NCT];
-#pragma unroll
-            for (int c = 0; c < NCT; ++c) {
-                const int kx = t * NCT + c;
-                a[c].x = a[c].y = x[c].x = x[c].y = T(0);
-                if (kx < Nh) {
-                    const C zk = W[fft_pad(kx, padsh)];
-                    const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, padsh)];
-                    a[c].x = (zk.x + zm.x) * sep_scale;   // Z[k] + conj(Z[-k])
-                    a[c].y = (zk.y - zm.y) * sep_scale;
-                    x[c].x = (zk.y + zm.y) * sep_scale;   // (Z[k] - conj(Z[-k])) / i
-                    x[c].y = (zm.x - zk.x) * sep_scale;
-                }
-            }
-            C* dst = Tdst + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
-#pragma unroll
-            for (int c = 0; c < NCT; ++c) { dst[c] = a[c]; dst[NCT + c] = x[c]; }
-        }
-        __syncthreads();
-    };
-
     if (MODE == LPC_ROWS_IFFT_ONLY) {
         for (int i = i0; i < i1; ++i) {
-            load_ifft_row(i, Vr, HVr);
+            rows_gather_ifft<T, SEQ>(TinP, tile_stride, i, NT, W, tw, Vr, HVr, tid);
             T* Vout = VH + base + (int64_t)i * Wp;
             T* HVout = VH + (int64_t)f.n_planes * plane + base + (int64_t)i * Wp;
             for (int j = tid; j < Wp; j += NTH) { Vout[j] = Vr[j]; HVout[j] = HVr[j]; }
@@ -157,57 +178,110 @@ k_admm_rows(FusedK f, AdmmK<T> k, FftPlan plan, const typename CxT<T>::type* __r
         for (int i = i0; i < i1; ++i) {
             const T* Vin = VH + base + (int64_t)i * Wp;
             const T* HVin = VH + (int64_t)f.n_planes * plane + base + (int64_t)i * Wp;
-            for (int j = tid; j < Wp; j += NTH) { C z; z.x = Vin[j]; z.y = HVin[j]; W[fft_pad(j, padsh)] = z; }
+            for (int j = tid; j < Wp; j += NTH) { C z; z.x = Vin[j]; z.y = HVin[j]; W[fft_pad(j, PADSH)] = z; }
             __syncthreads();
-            fft_store_row(i, const_cast<C*>(TinP));
+            rows_fft_store<T, SEQ>(W, tw, const_cast<C*>(TinP), tile_stride, i, NT, sep_scale, tid);
         }
         return;
     }
 
     // ------------------------------------------------------------------ FULL: the ADMM row step
+    // step s loads row i0-1+s into ring slot s%3 (V) and s%2 (HV); from s = 2 on, row i = i0+s-2 has
+    // its three V rows resident and is updated, transformed and stored.
     const int64_t eta1_off = (int64_t)k.n_planes * plane;
     const T* dp = data + (int64_t)data_plane_of(p, k) * k.dplane;
-    int sp = 0, sc = 1, sn = 2;  // ring slots of rows i-1, i, i+1
-    load_ifft_row(i0 == 0 ? Hp - 1 : i0 - 1, Vr + sp * wp4, nullptr);
-    load_ifft_row(i0, Vr + sc * wp4, HVr);
-    int hc = 0;  // HVr slot of row i
-    for (int i = i0; i < i1; ++i) {
+    const int nsteps = (i1 - i0) + 2;
+    for (int s = 0; s < nsteps; ++s) {
+        int r = i0 - 1 + s;
+        r = (r < 0) ? r + Hp : (r >= Hp ? r - Hp : r);
+        rows_gather_ifft<T, SEQ>(TinP, tile_stride, r, NT, W, tw, Vr + (s % 3) * wp4, HVr + (s & 1) * wp4, tid);
+        if (s < 2) continue;
+        const int i = i0 + s - 2;
         const int id = (i == Hp - 1) ? 0 : i + 1;
-        load_ifft_row(id, Vr + sn * wp4, HVr + (hc ^ 1) * wp4);
-        const T* Vp = Vr + sp * wp4;
-        const T* Vc = Vr + sc * wp4;
-        const T* Vn = Vr + sn * wp4;
-        const T* HVc = HVr + hc * wp4;
+        const T* Vp = Vr + ((s - 2) % 3) * wp4;
+        const T* Vc = Vr + ((s - 1) % 3) * wp4;
+        const T* Vn = Vr + (s % 3) * wp4;
+        const T* HVc = HVr + ((s - 1) & 1) * wp4;
         const int64_t ro = base + (int64_t)i * Wp;
         const int64_t rd = base + (int64_t)id * Wp;
         const bool row_in = (i >= k.sy) && (i < k.sy + k.h);
-        for (int j = tid; j < Wp; j += NTH) {
-            const int jl = (j == 0) ? Wp - 1 : j - 1;
-            const int jr = (j == Wp - 1) ? 0 : j + 1;
-            const T v = Vc[j];
-            T e0n, e1n, dummy;
-            const T t0 = tv_component(Vp[j] - v, eta_in[ro + j], k, e0n);
-            const T t1 = tv_component(Vc[jl] - v, eta_in[eta1_off + ro + j], k, e1n);
-            const T t0d = tv_component(v - Vn[j], eta_in[rd + j], k, dummy);
-            const T t1r = tv_component(v - Vc[jr], eta_in[eta1_off + ro + jr], k, dummy);
-            const bool inw = row_in && (j >= k.sx) && (j < k.sx + k.w);
-            T y = T(0);
-            if (inw) y = dp[(int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0)];
-            T xin, rhon;
-            point_update(v, HVc[j], y, inw, xi[ro + j], rho[ro + j], k, xin, rhon);
-            xi[ro + j] = xin;
-            rho[ro + j] = rhon;
-            eta_out[ro + j] = e0n;
-            eta_out[eta1_off + ro + j] = e1n;
-            C z;
-            z.x = -rhon + ((t0d - t0) + (t1r - t1));
-            z.y = xin;
-            W[fft_pad(j, padsh)] = z;
+        if constexpr (Wp % 4 == 0 && sizeof(T) == 4) {
+            // 128-bit path: a thread owns 4 consecutive pixels; all global accesses are float4
+            constexpr int NV = Wp / 4;
+            constexpr int IT = (NV + NTH - 1) / NTH;
+#pragma unroll 2
+            for (int it = 0; it < IT; ++it) {
+                const int q = tid + it * NTH;
+                if (q < NV) {
+                    const int j = 4 * q;
+                    const Vec16<T> e0 = ld16_nc(eta_in + ro + j);
+                    const Vec16<T> e0d = ld16_nc(eta_in + rd + j);
+                    const Vec16<T> e1 = ld16_nc(eta_in + eta1_off + ro + j);
+                    const Vec16<T> xih = ld16(xi + ro + j);
+                    const Vec16<T> rhoh = ld16(rho + ro + j);
+                    const int jr = (j + 4 == Wp) ? 0 : j + 4;
+                    const T e1r = __ldg(eta_in + eta1_off + ro + jr);
+                    Vec16<T> y;
+                    y.v[0] = y.v[1] = y.v[2] = y.v[3] = T(0);
+                    if (row_in && j >= k.dcol0 && j < k.dcol0 + k.dpitch)
+                        y = ld16_nc(dp + (int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0));
+                    const Vec16<T> vc = ld16(Vc + j), vp = ld16(Vp + j), vn = ld16(Vn + j), hv = ld16(HVc + j);
+                    const T vl = Vc[j == 0 ? Wp - 1 : j - 1];
+                    const T vr = Vc[jr];
+                    Vec16<T> t1, e1new, e0new, xin, rhon;
+                    T t0[4], t0d[4], dummy;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const T left = (e == 0) ? vl : vc.v[e - 1];
+                        t1.v[e] = tv_component<T, true>(left - vc.v[e], e1.v[e], k, e1new.v[e]);
+                        t0[e] = tv_component<T, true>(vp.v[e] - vc.v[e], e0.v[e], k, e0new.v[e]);
+                        t0d[e] = tv_component<T, true>(vc.v[e] - vn.v[e], e0d.v[e], k, dummy);
+                    }
+                    const T t1r = tv_component<T, true>(vc.v[3] - vr, e1r, k, dummy);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int jj = j + e;
+                        const bool inw = row_in && (jj >= k.sx) && (jj < k.sx + k.w);
+                        point_update<T, true>(vc.v[e], hv.v[e], y.v[e], inw, xih.v[e], rhoh.v[e], k, xin.v[e], rhon.v[e]);
+                        const T t1right = (e == 3) ? t1r : t1.v[e + 1];
+                        C z;
+                        z.x = -rhon.v[e] + ((t0d[e] - t0[e]) + (t1right - t1.v[e]));
+                        z.y = xin.v[e];
+                        W[fft_pad(jj, PADSH)] = z;
+                    }
+                    st16(xi + ro + j, xin);
+                    st16(rho + ro + j, rhon);
+                    st16(eta_out + ro + j, e0new);
+                    st16(eta_out + eta1_off + ro + j, e1new);
+                }
+            }
+        } else {
+            for (int j = tid; j < Wp; j += NTH) {
+                const int jl = (j == 0) ? Wp - 1 : j - 1;
+                const int jr = (j == Wp - 1) ? 0 : j + 1;
+                const T v = Vc[j];
+                T e0n, e1n, dummy;
+                const T t0 = tv_component<T, true>(Vp[j] - v, eta_in[ro + j], k, e0n);
+                const T t1 = tv_component<T, true>(Vc[jl] - v, eta_in[eta1_off + ro + j], k, e1n);
+                const T t0d = tv_component<T, true>(v - Vn[j], eta_in[rd + j], k, dummy);
+                const T t1r = tv_component<T, true>(v - Vc[jr], eta_in[eta1_off + ro + jr], k, dummy);
+                const bool inw = row_in && (j >= k.sx) && (j < k.sx + k.w);
+                T y = T(0);
+                if (inw) y = dp[(int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0)];
+                T xin, rhon;
+                point_update<T, true>(v, HVc[j], y, inw, xi[ro + j], rho[ro + j], k, xin, rhon);
+                xi[ro + j] = xin;
+                rho[ro + j] = rhon;
+                eta_out[ro + j] = e0n;
+                eta_out[eta1_off + ro + j] = e1n;
+                C z;
+                z.x = -rhon + ((t0d - t0) + (t1r - t1));
+                z.y = xin;
+                W[fft_pad(j, PADSH)] = z;
+            }
         }
         __syncthreads();
-        fft_store_row(i, ToutP);
-        const int tmp = sp; sp = sc; sc = sn; sn = tmp;
-        hc ^= 1;
+        rows_fft_store<T, SEQ>(W, tw, ToutP, tile_stride, i, NT, sep_scale, tid);
     }
 }
 
@@ -220,43 +294,43 @@ k_admm_rows(FusedK f, AdmmK<T> k, FftPlan plan, const typename CxT<T>::type* __r
 // Ht: [DC][NT][Hp][NCT] complex, Rt: same shape real (tile layout, built once per PSF).
 // grid (NT, planes)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int PPT>
-__global__ void __launch_bounds__(LPC_COLS_THREADS)
-k_admm_cols(FusedK f, FftPlan plan, const typename CxT<T>::type* __restrict__ tw,
-            const typename CxT<T>::type* __restrict__ Tsrc, typename CxT<T>::type* __restrict__ Tdst,
-            const typename CxT<T>::type* __restrict__ Ht, const T* __restrict__ Rt,
-            const typename CxT<T>::type* __restrict__ Sy, const typename CxT<T>::type* __restrict__ Sx) {
+template <typename T, typename SEQ>
+__global__ void __launch_bounds__(LPC_COLS_THREADS, 1)
+k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typename CxT<T>::type* __restrict__ Tsrc,
+            typename CxT<T>::type* __restrict__ Tdst, const typename CxT<T>::type* __restrict__ Ht,
+            const T* __restrict__ Rt, const typename CxT<T>::type* __restrict__ Sy,
+            const typename CxT<T>::type* __restrict__ Sx) {
     using C = typename CxT<T>::type;
-    constexpr int NTH = LPC_COLS_THREADS;
-    constexpr int NCT = LPC_NCT;
-    constexpr int NB = 2 * NCT;
+    constexpr int NTH = LPC_COLS_THREADS, NCT = LPC_NCT, NB = 2 * NCT;
+    constexpr int Hp = SEQ::N, PADSH = SEQ::padsh;
+    constexpr int n = Hp * NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* sm = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int Hp = f.Hp, NT = f.NT;
-    const int padsh = plan.padsh;
+    const int NT = f.NT;
     const int tile = blockIdx.x;
     const int p = blockIdx.y;
     const int q = p % f.DC;
-    const int n = Hp * NB;
     const C* src = Tsrc + ((int64_t)p * NT + tile) * n;
     C* dst = Tdst + ((int64_t)p * NT + tile) * n;
 
-    for (int e = tid; e < n; e += NTH) sm[fft_pad(e, padsh)] = src[e];
+#pragma unroll 4
+    for (int e = tid; e < n; e += NTH) sm[fft_pad(e, PADSH)] = src[e];
     __syncthreads();
-    cta_fft<T, -1, PPT>(sm, plan, tw, NB, 1, NB, tid, NTH);
+    CtaFftStatic<T, SEQ, -1, NB, NTH>::run(sm, tw, tid);
 
     const C* Hq = Ht + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
     const T* Rq = Rt + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
+#pragma unroll 2
     for (int e = tid; e < Hp * NCT; e += NTH) {
         const int ky = e / NCT, c = e - ky * NCT;
         const int kx = tile * NCT + c;
-        const int ia = fft_pad(ky * NB + c, padsh), ix = fft_pad(ky * NB + NCT + c, padsh);
+        const int ia = fft_pad(ky * NB + c, PADSH), ix = fft_pad(ky * NB + NCT + c, PADSH);
         const C A = sm[ia];
         const C Xi = sm[ix];
-        const C Hh = Hq[e];
-        const T Rn = Rq[e];
-        const C S = cx_mul(Sy[ky], Sx[kx < f.Nh ? kx : 0]);
+        const C Hh = __ldg(Hq + e);
+        const T Rn = __ldg(Rq + e);
+        const C S = cx_mul(__ldg(Sy + ky), __ldg(Sx + (kx < f.Nh ? kx : 0)));
         const C Hs = cx_mul(S, Hh);
         C Hc = Hh; Hc.y = -Hc.y;
         const C Hsa = cx_mul(S, Hc);
@@ -266,8 +340,9 @@ k_admm_cols(FusedK f, FftPlan plan, const typename CxT<T>::type* __restrict__ tw
         sm[ix] = cx_mul(Hs, Vh);
     }
     __syncthreads();
-    cta_fft<T, +1, PPT>(sm, plan, tw, NB, 1, NB, tid, NTH);
-    for (int e = tid; e < n; e += NTH) dst[e] = sm[fft_pad(e, padsh)];
+    CtaFftStatic<T, SEQ, +1, NB, NTH>::run(sm, tw, tid);
+#pragma unroll 4
+    for (int e = tid; e < n; e += NTH) dst[e] = sm[fft_pad(e, PADSH)];
 }
 
 // H, R (planar [DC][Hp][Nh]) -> tile layout [DC][NT][Hp][NCT]; Rn gets the 1/2 of the row separation
