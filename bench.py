@@ -314,7 +314,8 @@ def main():
     kernel_bytes = {
         "admm_spatial(K1)": 11.0 * P + d,        # v1: reads V,HV,xi',rho',eta'0,eta'1 (+y); writes xi',rho',eta'0,eta'1,a
         "admm_spectral(K2)": 5.5 * Sp,           # v1: reads A,Xi,H,R; writes Vhat,HVhat
-        "admm_rows(B)": 8.0 * P + 4.0 * Sp + d,  # v2: reads Tin(2Sp),xi',rho',eta'(2P) (+y); writes the same 4P and Tout(2Sp)
+        "rows_ifft(B1)": 2.0 * Sp + 2.0 * P,             # v2: reads Tin(2Sp); writes V,HV
+        "rows_spatial_fft(B2)": 10.0 * P + 2.0 * Sp + d,  # v2: reads V,HV,xi',rho',eta'(2P) (+y); writes xi',rho',eta'(2P),Tout(2Sp)
         "admm_cols(A)": 5.5 * Sp,                # v2: reads Tout(2Sp),H,R; writes Tin(2Sp)
         "update": 5.0 * d, "residual": 3.0 * d, "spec_mul_H": 3.0 * Sp, "spec_mul_Hadj": 3.0 * Sp,
     }
@@ -323,7 +324,7 @@ def main():
     kbytes = kernel_bytes[kname]
     engine = lib.lpc_engine_version(recon._plan)
     if args.algo == "admm":
-        own_launches = 2 * n_iter + 2 + (1 if engine == 2 else 0)  # 2 kernels / iteration, pack + unpack (+ row IFFT) per recon
+        own_launches = (3 if engine == 2 else 2) * n_iter + 2  # kernels / iteration, pack + unpack per recon
     else:
         own_launches = 4 * n_iter + 3
     k_ms = phases.get(kname, 0.0)
@@ -335,7 +336,7 @@ def main():
         "algorithmic_bytes_per_launch": kbytes, "launch_ms": k_ms,
         "phases_ms_per_iter": phases,
         "phases_GBs": {n: kernel_bytes[n] / (t * 1e-3) / 1e9 for n, t in own.items() if t > 0},
-        "engine": "v2 fused own-FFT (2 kernels / iteration)" if engine == 2 else "v1 K1/K2 + cuFFT",
+        "engine": "v2 fused own-FFT (3 kernels / iteration)" if engine == 2 else "v1 K1/K2 + cuFFT",
         "iteration": {
             "algorithmic_bytes": bytes_iter, "ms_ungraphed": iter_ms, "ms_in_step": ms_step / n_iter / Bg,
             "achieved_GBs": bytes_iter / (ms_step / n_iter * 1e-3) / 1e9,

@@ -56,17 +56,18 @@ template <> struct FftTraits<double> {
 
 // ---- compiled menu of the fused engine (float only): padded size -> kernel instantiation
 namespace {
-using RowsKern = void (*)(FusedK, AdmmK<float>, const float2*, const float2*, float2*, const float*, float*, float*,
-                          const float*, float*, float*, float);
+using IfftKern = void (*)(FusedK, const float2*, const float2*, float*);
+using FftKern = void (*)(FusedK, const float2*, const float*, float2*, float);
+using SpatKern = void (*)(FusedK, AdmmK<float>, const float2*, const float*, float2*, const float*, float*, float*,
+                          const float*, float*);
 using ColsKern = void (*)(FusedK, const float2*, const float2*, float2*, const float2*, const float*, const float2*,
                           const float2*);
-struct RowsEntry { int N, npass, radix[4]; RowsKern kern[3]; };
+struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial; };
 struct ColsEntry { int N, npass, radix[4]; ColsKern kern; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
-#define LPC_X(N, ...)                                                                                         \
-    {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__},                                                              \
-     {k_admm_rows<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_FULL>, k_admm_rows<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_IFFT_ONLY>, \
-      k_admm_rows<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_FFT_ONLY>}},
+#define LPC_X(N, ...)                                                                                   \
+    {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_rows_ifft<float, FftSeq<N, __VA_ARGS__>>,              \
+     k_rows_fft<float, FftSeq<N, __VA_ARGS__>>, k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_RY>},
 const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
 #undef LPC_X
 #define LPC_X(N, ...) {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_admm_cols<float, FftSeq<N, __VA_ARGS__>>},
@@ -170,7 +171,7 @@ struct Plan : lpc_plan_s {
     bool psf_set = false, data_set = false, state_ready = false, fista_first = true;
     // ---- graph cache (one entry)
     cudaGraphExec_t gexec = nullptr;
-    int g_niter = -1, g_eta = -1, g_first = -1;
+    int g_niter = -1, g_eta = -1, g_first = -1, g_vh = -1;
     double g_tk = 0;
     cudaStream_t g_stream = nullptr;
 
@@ -315,13 +316,27 @@ struct Plan : lpc_plan_s {
     const RowsEntry* rows_entry = nullptr;
     const ColsEntry* cols_entry = nullptr;
 
-    template <int MODE> int launch_rows(cudaStream_t st, const T* eta_i, T* eta_o, T sep_scale) {
+    int launch_rows_ifft(cudaStream_t st) {
         if constexpr (std::is_same<T, float>::value) {
-            const AdmmK<T> k = admm_k();
-            T* xi = AX + (int64_t)Np * plane;
-            const unsigned grid = (unsigned)(Np * fk.bands_per_plane);
-            rows_entry->kern[MODE]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, k, tw_row, Tin, Tout, data, xi, rho, eta_i,
-                                                                             eta_o, VH, sep_scale);
+            dim3 grid(Hp, Np);
+            rows_entry->ifft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, tw_row, Tin, VH);
+            LPC_KCHECK();
+        }
+        return LPC_OK;
+    }
+    int launch_rows_fft(cudaStream_t st, T sep_scale) {
+        if constexpr (std::is_same<T, float>::value) {
+            dim3 grid(Hp, Np);
+            rows_entry->fft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, tw_row, VH, Tin, sep_scale);
+            LPC_KCHECK();
+        }
+        return LPC_OK;
+    }
+    int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o) {
+        if constexpr (std::is_same<T, float>::value) {
+            dim3 grid((Hp + LPC_ROWS_RY - 1) / LPC_ROWS_RY, Np);
+            rows_entry->spatial<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, admm_k(), tw_row, VH, Tout, data,
+                                                                          AX + (int64_t)Np * plane, rho, eta_i, eta_o);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -346,33 +361,18 @@ struct Plan : lpc_plan_s {
             if (!rows_entry || !cols_entry) return LPC_OK;
             if (!make_fft_plan_from(Wp, rows_entry->radix, rows_entry->npass, &plan_row)) return LPC_OK;
             if (!make_fft_plan_from(Hp, cols_entry->radix, cols_entry->npass, &plan_col)) return LPC_OK;
-            const int wlen = fft_padded_len(Wp, plan_row.padsh);
-            const int wp4 = (Wp + 3) & ~3;
-            smem_row = (size_t)((wlen + 1) & ~1) * sizeof(Cplx) + (size_t)5 * wp4 * sizeof(T);
+            smem_row = (size_t)((fft_padded_len(Wp, plan_row.padsh) + 1) & ~1) * sizeof(Cplx);
             smem_col = (size_t)fft_padded_len(2 * LPC_NCT * Hp, plan_col.padsh) * sizeof(Cplx);
             int max_optin = 0;
             LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
             if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
-            for (int m = 0; m < 3; ++m)
-                LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->kern[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
             LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
 
             fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;
             fk.n_planes = Np; fk.DC = DC;
-            // bands: about one wave of CTAs over the SMs (resident CTAs per SM from the occupancy API)
-            int sms = 148, occ = 1;
-            LPC_CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-            LPC_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rows_entry->kern[LPC_ROWS_FULL], LPC_ROWS_THREADS, smem_row));
-            if (occ < 1) return LPC_OK;
-            const char* env_rpb = getenv("LPC_ROWS_PER_BAND");
-            int target = sms * occ / Np;
-            if (target < 1) target = 1;
-            int rpb = (Hp + target - 1) / target;
-            if (rpb < 8) rpb = Hp < 8 ? Hp : 8;
-            if (env_rpb) rpb = atoi(env_rpb) > 0 ? atoi(env_rpb) : rpb;
-            fk.rows_per_band = rpb;
-            fk.bands_per_plane = (Hp + rpb - 1) / rpb;
-
             int rc;
             const size_t tsz = (size_t)Np * fk.NT * Hp * 2 * LPC_NCT;
             if ((rc = alloc(&Tin, tsz))) return rc;
@@ -398,7 +398,7 @@ struct Plan : lpc_plan_s {
     // V, HV of the current iterate -> VH (they are not stored by the fused engine)
     int materialise_vh(cudaStream_t st) {
         if (!v2 || vh_valid) return LPC_OK;
-        int rc = launch_rows<LPC_ROWS_IFFT_ONLY>(st, eta[eta_cur], eta[eta_cur ^ 1], T(1));
+        int rc = launch_rows_ifft(st);
         if (rc) return rc;
         vh_valid = true;
         return LPC_OK;
@@ -607,7 +607,7 @@ struct Plan : lpc_plan_s {
                                                           rho, eta[0]);
                 LPC_KCHECK();
                 if (v2) {  // row spectra of (V, HV)/Wp into Tin
-                    if ((rc = launch_rows<LPC_ROWS_FFT_ONLY>(st, eta[0], eta[1], (T)(0.5 / (double)Wp)))) return rc;
+                    if ((rc = launch_rows_fft(st, (T)(0.5 / (double)Wp)))) return rc;
                     vh_valid = true;
                 }
             }
@@ -635,13 +635,15 @@ struct Plan : lpc_plan_s {
 #define LPC_EV(i) do { if (ev) LPC_CK(cudaEventRecord(ev[i], st)); } while (0)
         LPC_EV(0);
         if (v2) {
-            int rc = launch_rows<LPC_ROWS_FULL>(st, eta[eta_cur], eta[eta_cur ^ 1], T(1));
+            int rc = materialise_vh(st);  // B1: row IFFT -> V, HV (skipped when VH already holds them, e.g. after reset)
             if (rc) return rc;
+            LPC_EV(1);
+            if ((rc = launch_rows_spatial(st, eta[eta_cur], eta[eta_cur ^ 1]))) return rc;  // B2
             eta_cur ^= 1;
             vh_valid = false;
-            LPC_EV(1);
-            if ((rc = launch_cols(st))) return rc;
             LPC_EV(2);
+            if ((rc = launch_cols(st))) return rc;  // A
+            LPC_EV(3);
             return LPC_OK;
         }
         const AdmmK<T> k = admm_k();
@@ -720,7 +722,7 @@ struct Plan : lpc_plan_s {
         LPC_CK(cudaSetDevice(device));
         if (have_fwd) LPC_CF(cufftSetStream(fwd, st));
         if (have_inv) LPC_CF(cufftSetStream(inv, st));
-        const int np = (algo == LPC_ALGO_ADMM) ? (v2 ? 2 : 4) : 8;
+        const int np = (algo == LPC_ALGO_ADMM) ? (v2 ? 3 : 4) : 8;
         cudaEvent_t ev[9];
         for (int i = 0; i <= np; ++i) LPC_CK(cudaEventCreate(&ev[i]));
         for (int i = 0; i < np; ++i) ms[i] = 0.0;
@@ -761,7 +763,8 @@ struct Plan : lpc_plan_s {
         if (!use_graph) return iterate(n_iter, st);
 
         const int first = fista_first ? 1 : 0;
-        const bool hit = gexec && g_niter == n_iter && g_eta == eta_cur && g_stream == st &&
+        const int vh0 = vh_valid ? 1 : 0;  // the first captured iteration skips B1 when VH already holds V, HV
+        const bool hit = gexec && g_niter == n_iter && g_eta == eta_cur && g_stream == st && g_vh == vh0 &&
                          (algo != LPC_ALGO_FISTA || (g_tk == tk && g_first == first));
         if (!hit) {
             drop_graph();
@@ -776,7 +779,7 @@ struct Plan : lpc_plan_s {
             e = cudaGraphInstantiate(&gexec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { gexec = nullptr; return fail(LPC_ECUDA, "cudaGraphInstantiate", cudaGetErrorString(e)); }
-            g_niter = n_iter; g_eta = eta0; g_tk = tk_start; g_first = first; g_stream = st;
+            g_niter = n_iter; g_eta = eta0; g_tk = tk_start; g_first = first; g_stream = st; g_vh = vh0;
             // iterate() advanced the host-side bookkeeping while capturing; nothing ran yet
         } else {
             // replay: advance the host-side bookkeeping exactly as iterate() would
@@ -882,7 +885,7 @@ struct Plan : lpc_plan_s {
     }
     int launches_per_iter(int* total, int* own) override {
         int o = 0, f = 0;
-        if (algo == LPC_ALGO_ADMM) { o = 2; f = v2 ? 0 : 2; }
+        if (algo == LPC_ALGO_ADMM) { o = v2 ? 3 : 2; f = v2 ? 0 : 2; }
         else if (algo >= LPC_ALGO_GD) { o = 4; f = 4; }
         else { o = 3; f = 2; }
         if (own) *own = o;
@@ -893,9 +896,9 @@ struct Plan : lpc_plan_s {
     int engine_version() override { return v2 ? 2 : 1; }
     const char* phase_name(int phase) override {
         static const char* admm1[] = {"admm_spatial(K1)", "cufft_r2c", "admm_spectral(K2)", "cufft_c2r"};
-        static const char* admm2[] = {"admm_rows(B)", "admm_cols(A)"};
+        static const char* admm2[] = {"rows_ifft(B1)", "rows_spatial_fft(B2)", "admm_cols(A)"};
         static const char* gd[] = {"cufft_r2c", "spec_mul_H", "cufft_c2r", "residual", "cufft_r2c", "spec_mul_Hadj", "cufft_c2r", "update"};
-        if (algo == LPC_ALGO_ADMM && v2 && phase >= 0 && phase < 2) return admm2[phase];
+        if (algo == LPC_ALGO_ADMM && v2 && phase >= 0 && phase < 3) return admm2[phase];
         if (algo == LPC_ALGO_ADMM && !v2 && phase >= 0 && phase < 4) return admm1[phase];
         if (algo >= LPC_ALGO_GD && phase >= 0 && phase < 8) return gd[phase];
         return "";

@@ -1,16 +1,16 @@
-// lpc_fused.cuh -- engine v2: the whole ADMM iteration in TWO kernels, transforms included.
+// lpc_fused.cuh -- engine v2: the ADMM iteration in THREE kernels, all transforms hand-written and fused with the
+// element-wise work on either side of them:
 //
-//   k_admm_rows  (B): row IFFT -> K1 spatial primal/dual update -> row FFT      [per band of rows]
-//   k_admm_cols  (A): column FFT -> K2 spectral update -> column IFFT           [per tile of columns]
+//   k_rows_ifft        (B1): gather Tin -> row IFFT -> V, HV                      [one row per CTA]
+//   k_rows_spatial_fft (B2): K1 spatial primal/dual update -> row FFT -> Tout     [RY rows per CTA]
+//   k_admm_cols        (A) : column FFT -> K2 spectral update -> column IFFT      [one tile per CTA]
 //
-// V and HV are never stored: they only exist inside B, between its inverse and forward row
-// transforms.  What persists between iterations is
-//   duals  xi', rho', eta' (spatial, planar)                                     4P
-//   Tin    row spectra of (V, HV)/Wp  after A's column IFFT                       2Sp
-//   Tout   row spectra of 2*(a, xi')  after B's row FFT                           2Sp
-// so one iteration moves  B: 2Sp + 4P (+ the eta'0 halo row, L2) + d in, 4P + 2Sp out;
-// A: 2Sp + H + R in, 2Sp out  =  8P + 9.5Sp + d  ~ 1.77 GB at 3x1080x1920 (v1 with cuFFT: ~3.3 GB;
-// SURVEY's canonical figure 16P + 9.5Sp + d = 2.56 GB counts a, V, HV materialised).
+// HBM traffic per iteration: B1 2Sp in, 2P out; B2 2P + 4P + d in (V's +-1 rows and eta'0's +1 row
+// come from L2), 4P + 2Sp out; A 2Sp + H + R in, 2Sp out  =  12P + 9.5Sp + d ~ 2.17 GB at
+// 3x1080x1920 (v1 with cuFFT measured ~3.3 GB; `a`, `bq`, and the un-tangled real spectra never
+// reach HBM).  A first version kept V/HV on chip in one fused row kernel (8P + 9.5Sp + d); its
+// 107 KB of shared memory per CTA left 16 warps per SM and the kernel latency-bound at
+// 0.88 ms (profiles/r01_ncu_full_v2_fused_rows_cols_raw.csv) -- splitting it buys occupancy.
 //
 // Two real rows per complex transform: B packs z = a + i*xi' (forward) and Y = Vhat + i*HVhat
 // (inverse) so every row transform is ONE complex FFT of length Wp (any parity of Wp), with
@@ -55,44 +55,7 @@ struct FusedK {
     int rows_per_band, bands_per_plane;
 };
 
-enum { LPC_ROWS_FULL = 0, LPC_ROWS_IFFT_ONLY = 1, LPC_ROWS_FFT_ONLY = 2 };
-
-// ---- B helper: gather one row of Tin into W as the full-length complex row Y = Vhat + i*HVhat
-//      (Hermitian extension for kx > Wp/2), inverse FFT, scatter to the real rows
-template <typename T, typename SEQ>
-__device__ __forceinline__ void rows_gather_ifft(const typename CxT<T>::type* __restrict__ TinP, int64_t tile_stride,
-                                                 int row, int NT, typename CxT<T>::type* W,
-                                                 const typename CxT<T>::type* __restrict__ tw, T* Vdst, T* HVdst, int tid) {
-    using C = typename CxT<T>::type;
-    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
-    for (int t = tid; t < NT; t += NTH) {
-        const C* src = TinP + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
-        C vh[NCT], hh[NCT];
-#pragma unroll
-        for (int c = 0; c < NCT; ++c) { vh[c] = src[c]; hh[c] = src[NCT + c]; }
-#pragma unroll
-        for (int c = 0; c < NCT; ++c) {
-            const int kx = t * NCT + c;
-            if (kx < Nh) {
-                C y; y.x = vh[c].x - hh[c].y; y.y = vh[c].y + hh[c].x;
-                W[fft_pad(kx, PADSH)] = y;
-                const int m = Wp - kx;
-                if (kx >= 1 && m >= Nh) {
-                    C ym; ym.x = vh[c].x + hh[c].y; ym.y = hh[c].x - vh[c].y;
-                    W[fft_pad(m, PADSH)] = ym;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    CtaFftStatic<T, SEQ, +1, 1, NTH>::run(W, tw, tid);
-    for (int j = tid; j < Wp; j += NTH) {
-        const C c = W[fft_pad(j, PADSH)];
-        Vdst[j] = c.x;
-        if (HVdst) HVdst[j] = c.y;
-    }
-    __syncthreads();
-}
+constexpr int LPC_ROWS_RY = 4;  // rows a B2 CTA processes back to back
 
 // ---- B helper: forward FFT of the row held in W (z = a + i*xi'), separate the two real spectra
 //      and store the half spectrum to row `row` of Tdst (T-layout)
@@ -126,87 +89,143 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
 }
 
 // ---------------------------------------------------------------------------------------------
-// B: one CTA marches down a band of rows of one plane.
-// shared memory:  W   complex[padded Wp]   row transform, in place
-//                 Vr  real[3][Wp]          rolling window of V rows i-1, i, i+1
-//                 HVr real[2][Wp]          HV rows i, i+1
-// MODE FULL      : the ADMM row step.
-// MODE IFFT_ONLY : only materialise V, HV (planar spatial, VH[2][planes][Hp][Wp]) -- _form_image / debug.
-// MODE FFT_ONLY  : only transform given V, HV into Tin (warm start, admm.py:154-155,172-176).
+// B1: row IFFT.  One CTA per row: gather the row of Tin, inverse FFT in shared memory, write the
+// V row and the HV row (planar spatial, VH[2][planes][Hp][Wp]).  30 KB of shared memory per CTA at
+// Wp = 3840, so several CTAs per SM hide the gather latency.        grid (Hp, planes)
+// Also what _form_image / lpc_get_state use to materialise V and HV.
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename SEQ, int MODE>
-__global__ void __launch_bounds__(LPC_ROWS_THREADS, 2)
-k_admm_rows(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict__ tw,
-            const typename CxT<T>::type* __restrict__ Tin, typename CxT<T>::type* __restrict__ Tout,
-            const T* __restrict__ data, T* __restrict__ xi, T* __restrict__ rho, const T* __restrict__ eta_in,
-            T* __restrict__ eta_out, T* __restrict__ VH, T sep_scale) {
+template <typename T, typename SEQ>
+__global__ void __launch_bounds__(LPC_ROWS_THREADS, 3)
+k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typename CxT<T>::type* __restrict__ Tin,
+            T* __restrict__ VH) {
     using C = typename CxT<T>::type;
-    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT;
-    constexpr int Wp = SEQ::N, PADSH = SEQ::padsh;
-    constexpr int wlen = Wp + (Wp >> PADSH) + 1;
-    constexpr int wp4 = (Wp + 3) & ~3;  // keep the real rows 16-byte aligned
+    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
+    constexpr int NT = (Nh + NCT - 1) / NCT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int Hp = f.Hp, NT = f.NT;
     C* W = reinterpret_cast<C*>(smem_raw);
-    T* Vr = reinterpret_cast<T*>(W + ((wlen + 1) & ~1));
-    T* HVr = Vr + 3 * wp4;
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x, p = blockIdx.y;
+    const int Hp = f.Hp;
+    const int64_t tile_stride = (int64_t)Hp * (2 * NCT);
+    const C* src0 = Tin + (int64_t)p * NT * tile_stride + (int64_t)row * (2 * NCT);
+    constexpr int IT = (NT + NTH - 1) / NTH;
+    // all 32-byte chunks of the row in flight at once
+    Vec16<T> c0[IT], c1[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int t = tid + it * NTH;
+        if (t < NT) {
+            const T* s = reinterpret_cast<const T*>(src0 + (int64_t)t * tile_stride);
+            c0[it] = ld16_nc(s);
+            c1[it] = ld16_nc(s + 16 / sizeof(T));
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int t = tid + it * NTH;
+        if (t < NT) {
+            // c0 = (Vhat[kx], Vhat[kx+1]), c1 = (HVhat[kx], HVhat[kx+1])   (float: 2 complex per 16 B)
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) {
+                const int kx = t * NCT + c;
+                C vh, hh;
+                vh.x = c0[it].v[2 * c]; vh.y = c0[it].v[2 * c + 1];
+                hh.x = c1[it].v[2 * c]; hh.y = c1[it].v[2 * c + 1];
+                if (kx < Nh) {
+                    C y; y.x = vh.x - hh.y; y.y = vh.y + hh.x;
+                    W[fft_pad(kx, PADSH)] = y;
+                    const int m = Wp - kx;
+                    if (kx >= 1 && m >= Nh) {
+                        C ym; ym.x = vh.x + hh.y; ym.y = hh.x - vh.y;
+                        W[fft_pad(m, PADSH)] = ym;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    CtaFftStatic<T, SEQ, +1, 1, NTH>::run(W, tw, tid);
+    const int64_t plane = (int64_t)Hp * Wp;
+    T* Vout = VH + (int64_t)p * plane + (int64_t)row * Wp;
+    T* HVout = Vout + (int64_t)f.n_planes * plane;
+    if constexpr (Wp % 4 == 0 && sizeof(T) == 4) {
+        for (int q = tid; q < Wp / 4; q += NTH) {
+            Vec16<T> a, b;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const C c = W[fft_pad(4 * q + e, PADSH)]; a.v[e] = c.x; b.v[e] = c.y; }
+            st16(Vout + 4 * q, a);
+            st16(HVout + 4 * q, b);
+        }
+    } else {
+        for (int j = tid; j < Wp; j += NTH) { const C c = W[fft_pad(j, PADSH)]; Vout[j] = c.x; HVout[j] = c.y; }
+    }
+}
 
-    const int p = blockIdx.x / f.bands_per_plane;
-    const int band = blockIdx.x - p * f.bands_per_plane;
-    const int i0 = band * f.rows_per_band;
-    if (i0 >= Hp) return;
-    const int i1 = (i0 + f.rows_per_band < Hp) ? i0 + f.rows_per_band : Hp;
+// warm start (admm.py:154-155,172-176): given V, HV (planar) write their row spectra / Wp into Tin
+template <typename T, typename SEQ>
+__global__ void __launch_bounds__(LPC_ROWS_THREADS, 3)
+k_rows_fft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const T* __restrict__ VH,
+           typename CxT<T>::type* __restrict__ Tin, T sep_scale) {
+    using C = typename CxT<T>::type;
+    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
+    constexpr int NT = (Nh + NCT - 1) / NCT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* W = reinterpret_cast<C*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int row = blockIdx.x, p = blockIdx.y;
+    const int64_t plane = (int64_t)f.Hp * Wp;
+    const T* Vin = VH + (int64_t)p * plane + (int64_t)row * Wp;
+    const T* HVin = Vin + (int64_t)f.n_planes * plane;
+    for (int j = tid; j < Wp; j += NTH) { C z; z.x = Vin[j]; z.y = HVin[j]; W[fft_pad(j, PADSH)] = z; }
+    __syncthreads();
+    const int64_t tile_stride = (int64_t)f.Hp * (2 * NCT);
+    rows_fft_store<T, SEQ>(W, tw, Tin + (int64_t)p * NT * tile_stride, tile_stride, row, NT, sep_scale, tid);
+}
 
+// ---------------------------------------------------------------------------------------------
+// B2: the K1 spatial primal/dual update fused with the forward row FFT.  A CTA takes RY consecutive
+// rows of one plane, one after the other: per row it reads V (3 rows), HV, the half duals and the
+// measurement with 128-bit loads, writes the new half duals, puts z = a + i*xi' into shared memory,
+// transforms it and stores the separated half spectra to Tout.  `a` and `bq` never reach HBM.
+// grid (ceil(Hp/RY), planes)
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename SEQ, int RY>
+__global__ void __launch_bounds__(LPC_ROWS_THREADS, 3)
+k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict__ tw, const T* __restrict__ VH,
+                   typename CxT<T>::type* __restrict__ Tout, const T* __restrict__ data, T* __restrict__ xi,
+                   T* __restrict__ rho, const T* __restrict__ eta_in, T* __restrict__ eta_out) {
+    using C = typename CxT<T>::type;
+    constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
+    constexpr int NT = (Nh + NCT - 1) / NCT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* W = reinterpret_cast<C*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int p = blockIdx.y;
+    const int Hp = f.Hp;
     const int64_t plane = (int64_t)Hp * Wp;
     const int64_t base = (int64_t)p * plane;
-    const int64_t tile_stride = (int64_t)Hp * (2 * NCT);  // complex elements per tile
-    const C* TinP = Tin + (int64_t)p * NT * tile_stride;
+    const int64_t eta1_off = (int64_t)k.n_planes * plane;
+    const T* V = VH + base;
+    const T* HV = VH + (int64_t)f.n_planes * plane + base;
+    const T* eta0 = eta_in + base;
+    const T* eta1 = eta_in + eta1_off + base;
+    T* eta0_o = eta_out + base;
+    T* eta1_o = eta_out + eta1_off + base;
+    T* xip = xi + base;
+    T* rhop = rho + base;
+    const T* dp = data + (int64_t)data_plane_of(p, k) * k.dplane;
+    const int64_t tile_stride = (int64_t)Hp * (2 * NCT);
     C* ToutP = Tout + (int64_t)p * NT * tile_stride;
 
-    if (MODE == LPC_ROWS_IFFT_ONLY) {
-        for (int i = i0; i < i1; ++i) {
-            rows_gather_ifft<T, SEQ>(TinP, tile_stride, i, NT, W, tw, Vr, HVr, tid);
-            T* Vout = VH + base + (int64_t)i * Wp;
-            T* HVout = VH + (int64_t)f.n_planes * plane + base + (int64_t)i * Wp;
-            for (int j = tid; j < Wp; j += NTH) { Vout[j] = Vr[j]; HVout[j] = HVr[j]; }
-            __syncthreads();
-        }
-        return;
-    }
-    if (MODE == LPC_ROWS_FFT_ONLY) {
-        for (int i = i0; i < i1; ++i) {
-            const T* Vin = VH + base + (int64_t)i * Wp;
-            const T* HVin = VH + (int64_t)f.n_planes * plane + base + (int64_t)i * Wp;
-            for (int j = tid; j < Wp; j += NTH) { C z; z.x = Vin[j]; z.y = HVin[j]; W[fft_pad(j, PADSH)] = z; }
-            __syncthreads();
-            rows_fft_store<T, SEQ>(W, tw, const_cast<C*>(TinP), tile_stride, i, NT, sep_scale, tid);
-        }
-        return;
-    }
-
-    // ------------------------------------------------------------------ FULL: the ADMM row step
-    // step s loads row i0-1+s into ring slot s%3 (V) and s%2 (HV); from s = 2 on, row i = i0+s-2 has
-    // its three V rows resident and is updated, transformed and stored.
-    const int64_t eta1_off = (int64_t)k.n_planes * plane;
-    const T* dp = data + (int64_t)data_plane_of(p, k) * k.dplane;
-    const int nsteps = (i1 - i0) + 2;
-    for (int s = 0; s < nsteps; ++s) {
-        int r = i0 - 1 + s;
-        r = (r < 0) ? r + Hp : (r >= Hp ? r - Hp : r);
-        rows_gather_ifft<T, SEQ>(TinP, tile_stride, r, NT, W, tw, Vr + (s % 3) * wp4, HVr + (s & 1) * wp4, tid);
-        if (s < 2) continue;
-        const int i = i0 + s - 2;
+    const int i0 = blockIdx.x * RY;
+    for (int r = 0; r < RY; ++r) {
+        const int i = i0 + r;
+        if (i >= Hp) break;
+        const int iu = (i == 0) ? Hp - 1 : i - 1;
         const int id = (i == Hp - 1) ? 0 : i + 1;
-        const T* Vp = Vr + ((s - 2) % 3) * wp4;
-        const T* Vc = Vr + ((s - 1) % 3) * wp4;
-        const T* Vn = Vr + (s % 3) * wp4;
-        const T* HVc = HVr + ((s - 1) & 1) * wp4;
-        const int64_t ro = base + (int64_t)i * Wp;
-        const int64_t rd = base + (int64_t)id * Wp;
+        const int64_t ro = (int64_t)i * Wp, ru = (int64_t)iu * Wp, rd = (int64_t)id * Wp;
         const bool row_in = (i >= k.sy) && (i < k.sy + k.h);
         if constexpr (Wp % 4 == 0 && sizeof(T) == 4) {
-            // 128-bit path: a thread owns 4 consecutive pixels; all global accesses are float4
             constexpr int NV = Wp / 4;
             constexpr int IT = (NV + NTH - 1) / NTH;
 #pragma unroll 2
@@ -214,20 +233,18 @@ k_admm_rows(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict__ tw,
                 const int q = tid + it * NTH;
                 if (q < NV) {
                     const int j = 4 * q;
-                    const Vec16<T> e0 = ld16_nc(eta_in + ro + j);
-                    const Vec16<T> e0d = ld16_nc(eta_in + rd + j);
-                    const Vec16<T> e1 = ld16_nc(eta_in + eta1_off + ro + j);
-                    const Vec16<T> xih = ld16(xi + ro + j);
-                    const Vec16<T> rhoh = ld16(rho + ro + j);
                     const int jr = (j + 4 == Wp) ? 0 : j + 4;
-                    const T e1r = __ldg(eta_in + eta1_off + ro + jr);
+                    const int jl = (j == 0) ? Wp - 1 : j - 1;
+                    const Vec16<T> vc = ld16_nc(V + ro + j), vp = ld16_nc(V + ru + j), vn = ld16_nc(V + rd + j);
+                    const Vec16<T> hv = ld16_nc(HV + ro + j);
+                    const Vec16<T> e0 = ld16_nc(eta0 + ro + j), e0d = ld16_nc(eta0 + rd + j), e1 = ld16_nc(eta1 + ro + j);
+                    const Vec16<T> xih = ld16(xip + ro + j), rhoh = ld16(rhop + ro + j);
+                    const T e1r = __ldg(eta1 + ro + jr);
+                    const T vl = __ldg(V + ro + jl), vr = __ldg(V + ro + jr);
                     Vec16<T> y;
                     y.v[0] = y.v[1] = y.v[2] = y.v[3] = T(0);
                     if (row_in && j >= k.dcol0 && j < k.dcol0 + k.dpitch)
                         y = ld16_nc(dp + (int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0));
-                    const Vec16<T> vc = ld16(Vc + j), vp = ld16(Vp + j), vn = ld16(Vn + j), hv = ld16(HVc + j);
-                    const T vl = Vc[j == 0 ? Wp - 1 : j - 1];
-                    const T vr = Vc[jr];
                     Vec16<T> t1, e1new, e0new, xin, rhon;
                     T t0[4], t0d[4], dummy;
 #pragma unroll
@@ -249,31 +266,31 @@ k_admm_rows(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict__ tw,
                         z.y = xin.v[e];
                         W[fft_pad(jj, PADSH)] = z;
                     }
-                    st16(xi + ro + j, xin);
-                    st16(rho + ro + j, rhon);
-                    st16(eta_out + ro + j, e0new);
-                    st16(eta_out + eta1_off + ro + j, e1new);
+                    st16(xip + ro + j, xin);
+                    st16(rhop + ro + j, rhon);
+                    st16(eta0_o + ro + j, e0new);
+                    st16(eta1_o + ro + j, e1new);
                 }
             }
         } else {
             for (int j = tid; j < Wp; j += NTH) {
                 const int jl = (j == 0) ? Wp - 1 : j - 1;
                 const int jr = (j == Wp - 1) ? 0 : j + 1;
-                const T v = Vc[j];
+                const T v = V[ro + j];
                 T e0n, e1n, dummy;
-                const T t0 = tv_component<T, true>(Vp[j] - v, eta_in[ro + j], k, e0n);
-                const T t1 = tv_component<T, true>(Vc[jl] - v, eta_in[eta1_off + ro + j], k, e1n);
-                const T t0d = tv_component<T, true>(v - Vn[j], eta_in[rd + j], k, dummy);
-                const T t1r = tv_component<T, true>(v - Vc[jr], eta_in[eta1_off + ro + jr], k, dummy);
+                const T t0 = tv_component<T, true>(V[ru + j] - v, eta0[ro + j], k, e0n);
+                const T t1 = tv_component<T, true>(V[ro + jl] - v, eta1[ro + j], k, e1n);
+                const T t0d = tv_component<T, true>(v - V[rd + j], eta0[rd + j], k, dummy);
+                const T t1r = tv_component<T, true>(v - V[ro + jr], eta1[ro + jr], k, dummy);
                 const bool inw = row_in && (j >= k.sx) && (j < k.sx + k.w);
                 T y = T(0);
                 if (inw) y = dp[(int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0)];
                 T xin, rhon;
-                point_update<T, true>(v, HVc[j], y, inw, xi[ro + j], rho[ro + j], k, xin, rhon);
-                xi[ro + j] = xin;
-                rho[ro + j] = rhon;
-                eta_out[ro + j] = e0n;
-                eta_out[eta1_off + ro + j] = e1n;
+                point_update<T, true>(v, HV[ro + j], y, inw, xip[ro + j], rhop[ro + j], k, xin, rhon);
+                xip[ro + j] = xin;
+                rhop[ro + j] = rhon;
+                eta0_o[ro + j] = e0n;
+                eta1_o[ro + j] = e1n;
                 C z;
                 z.x = -rhon + ((t0d - t0) + (t1r - t1));
                 z.y = xin;
@@ -281,7 +298,7 @@ k_admm_rows(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict__ tw,
             }
         }
         __syncthreads();
-        rows_fft_store<T, SEQ>(W, tw, ToutP, tile_stride, i, NT, sep_scale, tid);
+        rows_fft_store<T, SEQ>(W, tw, ToutP, tile_stride, i, NT, T(1), tid);
     }
 }
 
