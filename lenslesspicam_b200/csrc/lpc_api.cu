@@ -62,15 +62,18 @@ using SpatKern = void (*)(FusedK, AdmmK<float>, const float2*, const float*, flo
                           const float*, float*);
 using ColsKern = void (*)(FusedK, const float2*, const float2*, float2*, const float2*, const float*, const float2*,
                           const float2*);
-struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial; };
-struct ColsEntry { int N, npass, radix[4]; ColsKern kern; };
+struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; };
+struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
 #define LPC_X(N, ...)                                                                                   \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_rows_ifft<float, FftSeq<N, __VA_ARGS__>>,              \
-     k_rows_fft<float, FftSeq<N, __VA_ARGS__>>, k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, LPC_ROWS_RY>},
+     k_rows_fft<float, FftSeq<N, __VA_ARGS__>>,                                                         \
+     {k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 1>, k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 2>, \
+      k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 4>}},
 const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
 #undef LPC_X
-#define LPC_X(N, ...) {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_admm_cols<float, FftSeq<N, __VA_ARGS__>>},
+#define LPC_X(N, ...) \
+    {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, {k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 1024, 1>, k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>}},
 const ColsEntry g_cols_menu[] = {LPC_COL_MENU(LPC_X)};
 #undef LPC_X
 const RowsEntry* find_rows(int N) {
@@ -315,6 +318,8 @@ struct Plan : lpc_plan_s {
     // ---------------------------------------------------------------- engine v2 set-up
     const RowsEntry* rows_entry = nullptr;
     const ColsEntry* cols_entry = nullptr;
+    int ry_log2 = 0;       // B2 processes 1 << ry_log2 rows per CTA (measured: 1 row 315 us, 2 rows 400, 4 rows 465)
+    int cols_variant = 1;  // A: 0 = 1024 threads x 1 CTA/SM, 1 = 576 threads x 2 CTAs/SM
 
     int launch_rows_ifft(cudaStream_t st) {
         if constexpr (std::is_same<T, float>::value) {
@@ -334,8 +339,9 @@ struct Plan : lpc_plan_s {
     }
     int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o) {
         if constexpr (std::is_same<T, float>::value) {
-            dim3 grid((Hp + LPC_ROWS_RY - 1) / LPC_ROWS_RY, Np);
-            rows_entry->spatial<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, admm_k(), tw_row, VH, Tout, data,
+            const int ry = 1 << ry_log2;
+            dim3 grid((Hp + ry - 1) / ry, Np);
+            rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, admm_k(), tw_row, VH, Tout, data,
                                                                           AX + (int64_t)Np * plane, rho, eta_i, eta_o);
             LPC_KCHECK();
         }
@@ -344,7 +350,7 @@ struct Plan : lpc_plan_s {
     int launch_cols(cudaStream_t st) {
         if constexpr (std::is_same<T, float>::value) {
             dim3 grid(fk.NT, Np);
-            cols_entry->kern<<<grid, LPC_COLS_THREADS, smem_col, st>>>(fk, tw_col, Tout, Tin, Ht, Rt, Sy, Sx);
+            cols_entry->kern[cols_variant]<<<grid, cols_variant ? 576 : 1024, smem_col, st>>>(fk, tw_col, Tout, Tin, Ht, Rt, Sy, Sx);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -368,8 +374,12 @@ struct Plan : lpc_plan_s {
             if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
             LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
             LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-            LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-            LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            for (int v = 0; v < 3; ++v)
+                LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->spatial[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            for (int v = 0; v < 2; ++v)
+                LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            if (const char* e = getenv("LPC_RY")) { int r = atoi(e); ry_log2 = r >= 4 ? 2 : r >= 2 ? 1 : 0; }
+            if (const char* e = getenv("LPC_COLS_VARIANT")) cols_variant = atoi(e) ? 1 : 0;
 
             fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;
             fk.n_planes = Np; fk.DC = DC;

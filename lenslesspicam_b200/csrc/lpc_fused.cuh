@@ -37,7 +37,7 @@ namespace lpc {
 
 constexpr int LPC_NCT = 2;  // columns per tile and slot
 constexpr int LPC_ROWS_THREADS = 256;
-constexpr int LPC_COLS_THREADS = 1024;
+constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIANT=1) uses 576 threads x 2 CTAs/SM
 
 // padded sizes with a compiled fast path: X(N, radices...).  Rows = Wp, columns = Hp.
 // 3840x2160: 1080x1920 (headline); 2048x1536 / 1024x768 / 512x384: the bundled 3040x4056 data at
@@ -190,7 +190,7 @@ k_rows_fft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const T* __re
 // grid (ceil(Hp/RY), planes)
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename SEQ, int RY>
-__global__ void __launch_bounds__(LPC_ROWS_THREADS, 3)
+__global__ void __launch_bounds__(LPC_ROWS_THREADS, 4)
 k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict__ tw, const T* __restrict__ VH,
                    typename CxT<T>::type* __restrict__ Tout, const T* __restrict__ data, T* __restrict__ xi,
                    T* __restrict__ rho, const T* __restrict__ eta_in, T* __restrict__ eta_out) {
@@ -311,14 +311,14 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
 // Ht: [DC][NT][Hp][NCT] complex, Rt: same shape real (tile layout, built once per PSF).
 // grid (NT, planes)
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename SEQ>
-__global__ void __launch_bounds__(LPC_COLS_THREADS, 1)
+template <typename T, typename SEQ, int NTH, int MINB>
+__global__ void __launch_bounds__(NTH, MINB)
 k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typename CxT<T>::type* __restrict__ Tsrc,
             typename CxT<T>::type* __restrict__ Tdst, const typename CxT<T>::type* __restrict__ Ht,
             const T* __restrict__ Rt, const typename CxT<T>::type* __restrict__ Sy,
             const typename CxT<T>::type* __restrict__ Sx) {
     using C = typename CxT<T>::type;
-    constexpr int NTH = LPC_COLS_THREADS, NCT = LPC_NCT, NB = 2 * NCT;
+    constexpr int NCT = LPC_NCT, NB = 2 * NCT;
     constexpr int Hp = SEQ::N, PADSH = SEQ::padsh;
     constexpr int n = Hp * NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -331,13 +331,37 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     const C* src = Tsrc + ((int64_t)p * NT + tile) * n;
     C* dst = Tdst + ((int64_t)p * NT + tile) * n;
 
-#pragma unroll 4
-    for (int e = tid; e < n; e += NTH) sm[fft_pad(e, PADSH)] = src[e];
+    const C* Hq = Ht + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
+    const T* Rq = Rt + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
+    // the tile is one contiguous block: 16-byte loads, all of a thread's loads in flight before the
+    // first shared-memory store; H and R (needed after the forward FFT) are pulled into L2 meanwhile
+    {
+        constexpr int NV = n / 2;                       // 16-byte vectors (2 complex) in the tile
+        constexpr int IT = (NV + NTH - 1) / NTH;
+        Vec16<T> buf[IT];
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int v = tid + it * NTH;
+            if (v < NV) buf[it] = ld16_nc(reinterpret_cast<const T*>(src) + 4 * v);
+        }
+        for (int e = tid * 16; e < Hp * NCT; e += NTH * 16) {   // one prefetch per 128-byte line of H, per 64 B of R
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Hq + e));
+            if ((e & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(Rq + e));
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int v = tid + it * NTH;
+            if (v < NV) {
+                C a, b;
+                a.x = buf[it].v[0]; a.y = buf[it].v[1]; b.x = buf[it].v[2]; b.y = buf[it].v[3];
+                sm[fft_pad(2 * v, PADSH)] = a;
+                sm[fft_pad(2 * v + 1, PADSH)] = b;
+            }
+        }
+    }
     __syncthreads();
     CtaFftStatic<T, SEQ, -1, NB, NTH>::run(sm, tw, tid);
 
-    const C* Hq = Ht + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
-    const T* Rq = Rt + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
 #pragma unroll 2
     for (int e = tid; e < Hp * NCT; e += NTH) {
         const int ky = e / NCT, c = e - ky * NCT;
@@ -358,8 +382,12 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     }
     __syncthreads();
     CtaFftStatic<T, SEQ, +1, NB, NTH>::run(sm, tw, tid);
-#pragma unroll 4
-    for (int e = tid; e < n; e += NTH) dst[e] = sm[fft_pad(e, PADSH)];
+    for (int v = tid; v < n / 2; v += NTH) {
+        const C a = sm[fft_pad(2 * v, PADSH)], b = sm[fft_pad(2 * v + 1, PADSH)];
+        Vec16<T> o;
+        o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
+        st16(reinterpret_cast<T*>(dst) + 4 * v, o);
+    }
 }
 
 // H, R (planar [DC][Hp][Nh]) -> tile layout [DC][NT][Hp][NCT]; Rn gets the 1/2 of the row separation
