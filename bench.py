@@ -209,14 +209,12 @@ def main():
 
     import lenslesspicam_b200 as L
     from lenslesspicam_b200 import _lib
+    from lenslesspicam_b200 import dist as lpd
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = lpd.env_world()
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    lpd.init(backend="nccl", device=device)
 
     n_iter = args.n_iter or (100 if args.algo == "admm" else 300)
     h, w, C, Bg = args.height, args.width, args.channels, args.batch_per_gpu
@@ -225,10 +223,9 @@ def main():
     gen = torch.Generator().manual_seed(0)
     psf = torch.rand((1, h, w, C), generator=gen) ** 8
     psf = (psf / psf.norm()).to(device)
-    if world > 1:
-        if rank != 0:
-            psf.zero_()
-        dist.broadcast(psf, src=0)  # the only collective of the job: init-time, NVLink/NVSwitch
+    if world > 1 and rank != 0:
+        psf.zero_()
+    lpd.broadcast_psf(psf, src=0)  # the only collective of the job: init-time, NCCL over NVLink/NVSwitch
     gen = torch.Generator().manual_seed(1000 + rank)
     scene = (torch.rand((Bg, 1, h, w, C), generator=gen) ** 2).to(device)
     sim = L.RealFFTConvolve2D(psf, pad=True, norm="backward")
@@ -252,10 +249,7 @@ def main():
             stream.synchronize()  # the caller reads the image: a real end-to-end step ends on the host
 
         def barrier():
-            torch.cuda.synchronize(device)
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize(device)
+            lpd.barrier(device)
 
         def timed(fn, K):
             barrier()
@@ -265,10 +259,7 @@ def main():
                 fn()
             e1.record(stream)
             barrier()
-            ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            return float(ms.item())
+            return lpd.max_over_ranks(e0.elapsed_time(e1), device=device)
 
         for _ in range(max(args.warmup, 3)):
             step_device()
@@ -296,8 +287,7 @@ def main():
         bytes_iter = recon.bytes_per_iter()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        lpd.finalize()
         return
 
     total = world * Bg
@@ -362,8 +352,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, n_iter)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    lpd.finalize()
 
 
 if __name__ == "__main__":
