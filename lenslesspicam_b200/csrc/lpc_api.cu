@@ -16,6 +16,7 @@
 #include "lpc_admm.cuh"
 #include "lpc_fft_plan.h"
 #include "lpc_fused.cuh"
+#include "lpc_fused_gd.cuh"
 #include "lpc_gd.cuh"
 #include "lpc_setup.cuh"
 #include "lpc_util.cuh"
@@ -62,18 +63,24 @@ using SpatKern = void (*)(FusedK, AdmmK<float>, const float2*, const float*, flo
                           const float*, float*);
 using ColsKern = void (*)(FusedK, const float2*, const float2*, float2*, const float2*, const float*, const float2*,
                           const float2*);
-struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; };
-struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; };
+using GdRowsKern = void (*)(GdFusedK, const float2*, float2*, const float*, float*, float*, const float*, float, int);
+using GdColsKern = void (*)(GdFusedK, const float2*, float2*, const float2*);
+struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; GdRowsKern gd[5]; };
+struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
 #define LPC_X(N, ...)                                                                                   \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_rows_ifft<float, FftSeq<N, __VA_ARGS__>>,              \
      k_rows_fft<float, FftSeq<N, __VA_ARGS__>>,                                                         \
      {k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 1>, k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 2>, \
-      k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 4>}},
+      k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 4>},                                                       \
+     {k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 0>, k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 1>,                   \
+      k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 2>, k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 3>,                   \
+      k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 4>}},
 const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
 #undef LPC_X
 #define LPC_X(N, ...) \
-    {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, {k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 1024, 1>, k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>}},
+    {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, {k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 1024, 1>, k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>}, \
+     k_gd_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>},
 const ColsEntry g_cols_menu[] = {LPC_COL_MENU(LPC_X)};
 #undef LPC_X
 const RowsEntry* find_rows(int N) {
@@ -163,6 +170,12 @@ struct Plan : lpc_plan_s {
     FusedK fk{};
     size_t smem_row = 0, smem_col = 0;
     bool vh_valid = false;  // VH holds the V / HV of the current iterate
+    // engine v2 for the GD family (lpc_fused_gd.cuh)
+    bool gd2 = false;
+    Cplx* Tg = nullptr;     // G-layout spectral buffer [Np][NTg][h][4], updated in place
+    Cplx* Fg = nullptr;     // [2][DC][NTg][Hp][4]: S*H/(2N) and S*conj(H)/(2N)
+    T* xu = nullptr;        // [Np][h][w] image estimate, unpadded planar
+    GdFusedK gk{};
     // ---- cuFFT
     cufftHandle fwd_psf = 0, fwd = 0, inv = 0, fwd1 = 0, inv1 = 0;
     bool have_fwd_psf = false, have_fwd = false, have_inv = false, have_1 = false;
@@ -292,12 +305,21 @@ struct Plan : lpc_plan_s {
             if ((rc = alloc(&eta[1], (size_t)2 * Np * plane))) return rc;
             if ((rc = alloc(&Rn, (size_t)DC * splane))) return rc;
         } else {
-            if ((rc = alloc(&xpad, (size_t)Np * plane))) return rc;
-            if ((rc = alloc(&rpad, (size_t)Np * plane))) return rc;
-            if (algo != LPC_ALGO_CONV) {
-                if ((rc = alloc(&dpad, (size_t)Np * plane))) return rc;
-                if (algo != LPC_ALGO_GD)
-                    if ((rc = alloc(&mom, (size_t)Np * h * w))) return rc;
+            if (algo >= LPC_ALGO_GD && !(flags & LPC_FLAG_ENGINE_V1) && getenv("LPC_ENGINE_V1") == nullptr) {
+                if ((rc = init_gd2())) return rc;
+            }
+            if (gd2) {
+                nb = 0;
+                if ((rc = alloc(&xu, (size_t)Np * h * w))) return rc;
+                if ((rc = alloc(&mom, (size_t)Np * h * w))) return rc;
+            } else {
+                if ((rc = alloc(&xpad, (size_t)Np * plane))) return rc;
+                if ((rc = alloc(&rpad, (size_t)Np * plane))) return rc;
+                if (algo != LPC_ALGO_CONV) {
+                    if ((rc = alloc(&dpad, (size_t)Np * plane))) return rc;
+                    if (algo != LPC_ALGO_GD)
+                        if ((rc = alloc(&mom, (size_t)Np * h * w))) return rc;
+                }
             }
         }
         if (nb > 0 && (rc = alloc(&spec, (size_t)nb * splane))) return rc;
@@ -400,6 +422,85 @@ struct Plan : lpc_plan_s {
             return LPC_OK;
         }
     }
+    // ---------------------------------------------------------------- GD family on the fused engine
+    int init_gd2() {
+        if constexpr (!std::is_same<T, float>::value) {
+            return LPC_OK;
+        } else {
+            rows_entry = find_rows(Wp);
+            cols_entry = find_cols(Hp);
+            if (!rows_entry || !cols_entry) return LPC_OK;
+            if (!make_fft_plan_from(Wp, rows_entry->radix, rows_entry->npass, &plan_row)) return LPC_OK;
+            if (!make_fft_plan_from(Hp, cols_entry->radix, cols_entry->npass, &plan_col)) return LPC_OK;
+            smem_row = (size_t)((fft_padded_len(Wp, plan_row.padsh) + 1) & ~1) * sizeof(Cplx);
+            smem_col = (size_t)fft_padded_len(LPC_GNC * Hp, plan_col.padsh) * sizeof(Cplx);
+            int max_optin = 0;
+            LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+            if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
+            for (int m = 0; m < 5; ++m)
+                LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->gd[m], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->gd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
+            gk.Hp = Hp; gk.Wp = Wp; gk.Nh = Nh; gk.NTg = (Nh + LPC_GNC - 1) / LPC_GNC;
+            gk.h = h; gk.w = w; gk.sy = sy; gk.sx = sx;
+            gk.n_planes = Np; gk.DC = DC; gk.C = C; gk.D = D; gk.Dd = Dd;
+            int rc;
+            if ((rc = alloc(&Tg, (size_t)Np * gk.NTg * h * LPC_GNC))) return rc;
+            if ((rc = alloc(&Fg, (size_t)2 * DC * gk.NTg * Hp * LPC_GNC))) return rc;
+            std::vector<Cplx> tw;
+            fill_fft_twiddles(plan_row, &tw);
+            if ((rc = alloc(&tw_row, tw.size()))) return rc;
+            LPC_CK(cudaMemcpy(tw_row, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            fill_fft_twiddles(plan_col, &tw);
+            if ((rc = alloc(&tw_col, tw.size()))) return rc;
+            LPC_CK(cudaMemcpy(tw_col, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            gd2 = true;
+            return LPC_OK;
+        }
+    }
+    int gd2_rows(int mode, T scalar, int first, cudaStream_t st) {
+        if constexpr (std::is_same<T, float>::value) {
+            gk.Dd = Dd;
+            dim3 grid((h + 1) / 2, Np);
+            rows_entry->gd[mode]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(gk, tw_row, Tg, data, xu, mom, consts, scalar, first);
+            LPC_KCHECK();
+        }
+        return LPC_OK;
+    }
+    int gd2_cols(int adjoint, cudaStream_t st) {
+        if constexpr (std::is_same<T, float>::value) {
+            dim3 grid(gk.NTg, Np);
+            const Cplx* F = Fg + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
+            cols_entry->gd<<<grid, 576, smem_col, st>>>(gk, tw_col, Tg, F);
+            LPC_KCHECK();
+        }
+        return LPC_OK;
+    }
+    int gd2_iteration(cudaStream_t st, cudaEvent_t* ev) {
+#define LPC_EV(i) do { if (ev) LPC_CK(cudaEventRecord(ev[i], st)); } while (0)
+        int rc;
+        LPC_EV(0);
+        if ((rc = gd2_cols(0, st))) return rc;                       // convolve: columns
+        LPC_EV(1);
+        if ((rc = gd2_rows(LPC_GD_RESID, T(0), 0, st))) return rc;   // rows back, - y, rows forward
+        LPC_EV(2);
+        if ((rc = gd2_cols(1, st))) return rc;                       // deconvolve: columns
+        LPC_EV(3);
+        if (algo == LPC_ALGO_GD) {
+            rc = gd2_rows(LPC_GD_UPD_GD, T(0), 0, st);
+        } else if (algo == LPC_ALGO_NESTEROV) {
+            rc = gd2_rows(LPC_GD_UPD_NESTEROV, (T)nmu, 0, st);
+        } else {
+            const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;  // gd.py:238
+            rc = gd2_rows(LPC_GD_UPD_FISTA, (T)((tk - 1.0) / tn), fista_first ? 1 : 0, st);
+            tk = tn;
+            fista_first = false;
+        }
+        if (rc) return rc;
+        LPC_EV(4);
+#undef LPC_EV
+        return LPC_OK;
+    }
+
     int tile_HR(cudaStream_t st) {
         k_tile_HR<T><<<1184, 256, 0, st>>>(Hc, Rn, Ht, Rt, DC, Hp, Nh, fk.NT);
         LPC_KCHECK();
@@ -500,6 +601,10 @@ struct Plan : lpc_plan_s {
         }
         if ((rc = compute_alpha(st))) return rc;
         if (algo == LPC_ALGO_ADMM && (rc = compute_R(st))) return rc;
+        if (gd2) {
+            k_gd_tile_filter<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, Fg, DC, Hp, Wp, Nh, gk.NTg);
+            LPC_KCHECK();
+        }
         psf_set = true;
         state_ready = false;
         return LPC_OK;
@@ -623,14 +728,18 @@ struct Plan : lpc_plan_s {
             }
         } else {
             // gd.py:94-126
+            T* xdst = gd2 ? xu : xpad;
+            const int64_t xps = gd2 ? (int64_t)h * w : plane;
+            const int xpitch = gd2 ? w : Wp, xoy = gd2 ? 0 : sy, xox = gd2 ? 0 : sx;
             if (dev_init) {
-                if ((rc = pack((const T*)dev_init, contiguous(D, h, w, C), nullptr, Strides5{}, xpad, B, D, h, w, plane, Wp,
-                               sy, sx, st))) return rc;
+                if ((rc = pack((const T*)dev_init, contiguous(D, h, w, C), nullptr, Strides5{}, xdst, B, D, h, w, xps, xpitch,
+                               xoy, xox, st))) return rc;
             } else {
                 dim3 grid((w + 127) / 128, h, Np);
-                k_fill_x0<T><<<grid, 128, 0, st>>>(xpad, consts, C, h, w, plane, Wp, sy, sx);
+                k_fill_x0<T><<<grid, 128, 0, st>>>(xdst, consts, C, h, w, xps, xpitch, xoy, xox);
                 LPC_KCHECK();
             }
+            if (gd2 && (rc = gd2_rows(LPC_GD_INIT, T(0), 0, st))) return rc;  // row spectra of the initial estimate
             if (mom) LPC_CK(cudaMemsetAsync(mom, 0, (size_t)Np * h * w * sizeof(T), st));
             tk = tk0;            // gd.py:227-233
             fista_first = true;  // xk aliases x right after reset (gd.py:233)
@@ -686,6 +795,7 @@ struct Plan : lpc_plan_s {
     }
 
     int gd_iteration(cudaStream_t st, cudaEvent_t* ev = nullptr) {
+        if (gd2) return gd2_iteration(st, ev);
         const GdK k = gd_k();
         int rc;
         LPC_EV(0);
@@ -732,7 +842,7 @@ struct Plan : lpc_plan_s {
         LPC_CK(cudaSetDevice(device));
         if (have_fwd) LPC_CF(cufftSetStream(fwd, st));
         if (have_inv) LPC_CF(cufftSetStream(inv, st));
-        const int np = (algo == LPC_ALGO_ADMM) ? (v2 ? 3 : 4) : 8;
+        const int np = (algo == LPC_ALGO_ADMM) ? (v2 ? 3 : 4) : (gd2 ? 4 : 8);
         cudaEvent_t ev[9];
         for (int i = 0; i <= np; ++i) LPC_CK(cudaEventCreate(&ev[i]));
         for (int i = 0; i < np; ++i) ms[i] = 0.0;
@@ -811,6 +921,7 @@ struct Plan : lpc_plan_s {
         if (!dev_out) return fail(LPC_EINVAL, "get_image", "null output");
         LPC_CK(cudaSetDevice(device));
         if (algo == LPC_ALGO_ADMM) { int rc = materialise_vh(st); if (rc) return rc; }
+        if (gd2) return unpack(xu, (int64_t)h * w, w, 0, 0, (T*)dev_out, B * D, h, w, 1, st);
         const T* src = (algo == LPC_ALGO_ADMM) ? VH : xpad;
         return unpack(src, plane, Wp, sy, sx, (T*)dev_out, B * D, h, w, 1, st);
     }
@@ -841,8 +952,10 @@ struct Plan : lpc_plan_s {
             }
             return unpack(src, plane, Wp, 0, 0, (T*)dev_out, B * D, Hp, Wp, 0, st);
         }
-        if (algo >= LPC_ALGO_GD && which == LPC_STATE_IMAGE_EST)
+        if (algo >= LPC_ALGO_GD && which == LPC_STATE_IMAGE_EST) {
+            if (gd2) return unpack(xu, (int64_t)h * w, w, 0, 0, (T*)dev_out, B * D, h, w, 0, st);
             return unpack(xpad, plane, Wp, sy, sx, (T*)dev_out, B * D, h, w, 0, st);
+        }
         return fail(LPC_EINVAL, "get_state", "selector not available for this algorithm");
     }
     int get_H(void* dev_out, cudaStream_t st) override {
@@ -896,18 +1009,20 @@ struct Plan : lpc_plan_s {
     int launches_per_iter(int* total, int* own) override {
         int o = 0, f = 0;
         if (algo == LPC_ALGO_ADMM) { o = v2 ? 3 : 2; f = v2 ? 0 : 2; }
-        else if (algo >= LPC_ALGO_GD) { o = 4; f = 4; }
+        else if (algo >= LPC_ALGO_GD) { o = 4; f = gd2 ? 0 : 4; }
         else { o = 3; f = 2; }
         if (own) *own = o;
         if (total) *total = o + f;  // each cuFFT exec is at least one kernel
         return LPC_OK;
     }
     size_t plan_bytes() override { return total_bytes + work_bytes; }
-    int engine_version() override { return v2 ? 2 : 1; }
+    int engine_version() override { return (v2 || gd2) ? 2 : 1; }
     const char* phase_name(int phase) override {
         static const char* admm1[] = {"admm_spatial(K1)", "cufft_r2c", "admm_spectral(K2)", "cufft_c2r"};
         static const char* admm2[] = {"rows_ifft(B1)", "rows_spatial_fft(B2)", "admm_cols(A)"};
         static const char* gd[] = {"cufft_r2c", "spec_mul_H", "cufft_c2r", "residual", "cufft_r2c", "spec_mul_Hadj", "cufft_c2r", "update"};
+        static const char* gdf[] = {"gd_cols(H)", "gd_rows(residual)", "gd_cols(Hadj)", "gd_rows(update)"};
+        if (algo >= LPC_ALGO_GD && gd2 && phase >= 0 && phase < 4) return gdf[phase];
         if (algo == LPC_ALGO_ADMM && v2 && phase >= 0 && phase < 3) return admm2[phase];
         if (algo == LPC_ALGO_ADMM && !v2 && phase >= 0 && phase < 4) return admm1[phase];
         if (algo >= LPC_ALGO_GD && phase >= 0 && phase < 8) return gd[phase];

@@ -1,0 +1,258 @@
+// lpc_fused_gd.cuh -- engine v2 for the gradient-descent family (gd.py:62-241): one iteration
+//
+//     g = deconvolve(convolve(x) - y)                    (gd.py:128-130; 4 FFT pairs in the reference)
+//     x <- update(x, alpha*g)                            (gd.py:132-134, 183-188, 235-241)
+//
+// in FOUR kernels, every transform hand-written (lpc_fft.cuh) and fused with its neighbours:
+//
+//   k_gd_cols (forward) : column FFT  ->  * S*H/(2N)        -> column IFFT        [one tile / CTA]
+//   k_gd_rows RESID     : row IFFT -> crop, - y, zero-pad   -> row FFT            [two rows / CTA]
+//   k_gd_cols (adjoint) : column FFT  ->  * S*conj(H)/(2N)  -> column IFFT
+//   k_gd_rows UPDATE    : row IFFT -> crop, step + projection + momentum -> zero-pad -> row FFT
+//
+// (the row FFT of the new estimate is the first half of the next iteration's convolve; an INIT
+// launch does it once after reset).  Zero padding is exploited on both sides: only the h window
+// rows are ever transformed along rows, stored, or loaded; the column kernel fills the other
+// Hp - h rows of its shared-memory tile with zeros and stores only the window rows.
+//
+// Two real rows per complex row transform: rows 2r and 2r+1 of the window are packed as
+// real + i*imag, so h/2 complex FFTs of length Wp serve h rows (any parity of Wp, odd h handled).
+//
+// "G-layout" of the single spectral buffer Tg (updated in place by both kernels):
+//     complex index ((p*NTg + kx/4)*h + r)*4 + kx%4,   r = window row, NTg = ceil(Nh/4)
+// i.e. 32-byte chunks per (tile,row) for the row kernel, one contiguous h*32-byte block per tile for
+// the column kernel.  HBM traffic per iteration ~ 2*(H table) + 6*(h/Hp)*Sp + 5d = 0.55 GB at
+// 3x1080x1920, against 10d + 6Sp = 0.85 GB canonical and ~2 GB for cuFFT + kernels.
+#pragma once
+#include "lpc_fft.cuh"
+#include "lpc_fused.cuh"
+#include "lpc_util.cuh"
+
+namespace lpc {
+
+constexpr int LPC_GNC = 4;  // columns per tile of the G-layout
+
+struct GdFusedK {
+    int Hp, Wp, Nh, NTg;
+    int h, w, sy, sx;
+    int n_planes, DC, C, D, Dd;
+};
+
+enum { LPC_GD_INIT = 0, LPC_GD_RESID = 1, LPC_GD_UPD_GD = 2, LPC_GD_UPD_NESTEROV = 3, LPC_GD_UPD_FISTA = 4 };
+
+__device__ __forceinline__ int gdf_data_plane(int p, const GdFusedK& k) {
+    const int dc = k.D * k.C;
+    const int b = p / dc, rem = p - b * dc;
+    const int dep = rem / k.C, c = rem - dep * k.C;
+    return (b * k.Dd + (k.Dd == 1 ? 0 : dep)) * k.C + c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rows: one CTA per pair of window rows (ra = 2*pair, rb = ra + 1) of one plane.   grid (ceil(h/2), planes)
+//   x, mom, data are planar UNPADDED [planes][h][w]; consts[3C + c] = alpha_c (gd.py:108-112)
+//   scalar: Nesterov mu (gd.py:183-188) or FISTA beta = (t_k - 1)/t_{k+1} (gd.py:238-239)
+//   first : FISTA only -- right after reset() the reference's previous iterate aliases the stepped
+//           estimate (gd.py:233,236), mirrored
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename SEQ, int MODE>
+__global__ void __launch_bounds__(LPC_ROWS_THREADS, 4)
+k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT<T>::type* __restrict__ Tg,
+          const T* __restrict__ data, T* __restrict__ x, T* __restrict__ mom, const T* __restrict__ consts, T scalar,
+          int first) {
+    using C = typename CxT<T>::type;
+    constexpr int NTH = LPC_ROWS_THREADS, NC = LPC_GNC, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
+    constexpr int NTg = (Nh + NC - 1) / NC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* W = reinterpret_cast<C*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int p = blockIdx.y;
+    const int ra = 2 * blockIdx.x, rb = ra + 1;
+    const int h = f.h, w = f.w, sx = f.sx;
+    const bool has_b = rb < h;
+    const int64_t tile_stride = (int64_t)h * NC;  // complex elements per tile
+    C* Tp = Tg + (int64_t)p * NTg * tile_stride;
+
+    if (MODE != LPC_GD_INIT) {
+        // gather the two half-spectrum rows, build the full-length packed row Y_a + i*Y_b, inverse FFT
+        for (int t = tid; t < NTg; t += NTH) {
+            const C* sa = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC;
+            C ya[NC], yb[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                ya[c] = sa[c];
+                if (has_b) yb[c] = sa[NC + c]; else { yb[c].x = T(0); yb[c].y = T(0); }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int kx = t * NC + c;
+                if (kx < Nh) {
+                    C y; y.x = ya[c].x - yb[c].y; y.y = ya[c].y + yb[c].x;
+                    W[fft_pad(kx, PADSH)] = y;
+                    const int m = Wp - kx;
+                    if (kx >= 1 && m >= Nh) {
+                        C ym; ym.x = ya[c].x + yb[c].y; ym.y = yb[c].x - ya[c].y;
+                        W[fft_pad(m, PADSH)] = ym;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        CtaFftStatic<T, SEQ, +1, 1, NTH>::run(W, tw, tid);
+    }
+
+    // element-wise stage on the window columns; everything outside the window becomes the zero padding
+    const int64_t ia = ((int64_t)p * h + ra) * w, ib = ia + w;
+    const T alpha = (MODE >= LPC_GD_UPD_GD) ? consts[3 * f.C + p % f.C] : T(0);
+    const T* dpl = data + (int64_t)gdf_data_plane(p, f) * h * w;
+    for (int j = tid; j < Wp; j += NTH) {
+        C z; z.x = T(0); z.y = T(0);
+        const int col = j - sx;
+        if (col >= 0 && col < w) {
+            if (MODE == LPC_GD_INIT) {
+                z.x = x[ia + col];
+                if (has_b) z.y = x[ib + col];
+            } else {
+                const C g = W[fft_pad(j, PADSH)];
+                if (MODE == LPC_GD_RESID) {
+                    z.x = g.x - dpl[(int64_t)ra * w + col];          // crop(Hx) - y   (gd.py:129)
+                    if (has_b) z.y = g.y - dpl[(int64_t)rb * w + col];
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        if (s == 1 && !has_b) break;
+                        const int64_t o = (s == 0 ? ia : ib) + col;
+                        const T gs = (s == 0) ? g.x : g.y;
+                        T xn;
+                        if (MODE == LPC_GD_UPD_GD) {                  // gd.py:132-134
+                            const T v = x[o] - alpha * gs;
+                            xn = v > T(0) ? v : T(0);
+                        } else if (MODE == LPC_GD_UPD_NESTEROV) {     // gd.py:183-188
+                            const T p_prev = mom[o];
+                            const T p_new = scalar * p_prev - alpha * gs;
+                            mom[o] = p_new;
+                            const T v = x[o] + (-scalar * p_prev + (T(1) + scalar) * p_new);
+                            xn = v > T(0) ? v : T(0);
+                        } else {                                       // FISTA, gd.py:235-241
+                            const T zz = x[o] - alpha * gs;
+                            const T xk = zz > T(0) ? zz : T(0);
+                            const T prev = first ? zz : mom[o];
+                            mom[o] = xk;
+                            xn = xk + scalar * (xk - prev);
+                        }
+                        x[o] = xn;
+                        if (s == 0) z.x = xn; else z.y = xn;
+                    }
+                }
+            }
+        }
+        W[fft_pad(j, PADSH)] = z;
+    }
+    __syncthreads();
+
+    // forward FFT of the packed pair, separate, store the two half-spectrum rows (no 1/2: folded into the filter)
+    CtaFftStatic<T, SEQ, -1, 1, NTH>::run(W, tw, tid);
+    for (int t = tid; t < NTg; t += NTH) {
+        C a[NC], b[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int kx = t * NC + c;
+            a[c].x = a[c].y = b[c].x = b[c].y = T(0);
+            if (kx < Nh) {
+                const C zk = W[fft_pad(kx, PADSH)];
+                const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PADSH)];
+                a[c].x = zk.x + zm.x; a[c].y = zk.y - zm.y;   // Z[k] + conj(Z[-k])
+                b[c].x = zk.y + zm.y; b[c].y = zm.x - zk.x;   // (Z[k] - conj(Z[-k])) / i
+            }
+        }
+        C* da = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            da[c] = a[c];
+            if (has_b) da[NC + c] = b[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// columns: one CTA per tile of LPC_GNC columns, in place.   grid (NTg, planes)
+//   F: filter in tile layout [DC][NTg][Hp][4] = S*H/(2*Hp*Wp) (convolve) or S*conj(H)/(2*Hp*Wp)
+//   (deconvolve; the same shift S, rfft_convolve.py:195)
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename SEQ, int NTH, int MINB>
+__global__ void __launch_bounds__(NTH, MINB)
+k_gd_cols(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT<T>::type* __restrict__ Tg,
+          const typename CxT<T>::type* __restrict__ F) {
+    using C = typename CxT<T>::type;
+    constexpr int NC = LPC_GNC, Hp = SEQ::N, PADSH = SEQ::padsh;
+    constexpr int n = Hp * NC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* sm = reinterpret_cast<C*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x, p = blockIdx.y;
+    const int q = p % f.DC;
+    const int h = f.h, sy = f.sy;
+    C* blk = Tg + ((int64_t)p * f.NTg + tile) * (int64_t)h * NC;
+    const C* Fq = F + ((int64_t)q * f.NTg + tile) * (int64_t)n;
+
+    for (int e = tid * 16; e < n; e += NTH * 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(Fq + e));
+    // window rows from HBM (16-byte loads), zeros elsewhere
+    for (int v = tid; v < n / 2; v += NTH) {
+        const int row = v / (NC / 2);
+        C a, b;
+        a.x = a.y = b.x = b.y = T(0);
+        const int r = row - sy;
+        if (r >= 0 && r < h) {
+            const Vec16<T> d = ld16_nc(reinterpret_cast<const T*>(blk) + 4 * (v - sy * (NC / 2)));
+            a.x = d.v[0]; a.y = d.v[1]; b.x = d.v[2]; b.y = d.v[3];
+        }
+        sm[fft_pad(2 * v, PADSH)] = a;
+        sm[fft_pad(2 * v + 1, PADSH)] = b;
+    }
+    __syncthreads();
+    CtaFftStatic<T, SEQ, -1, NC, NTH>::run(sm, tw, tid);
+    for (int e = tid; e < n; e += NTH) {
+        const int i = fft_pad(e, PADSH);
+        sm[i] = cx_mul(sm[i], __ldg(Fq + e));
+    }
+    __syncthreads();
+    CtaFftStatic<T, SEQ, +1, NC, NTH>::run(sm, tw, tid);
+    for (int v = tid; v < h * (NC / 2); v += NTH) {
+        const int e = 2 * (v + sy * (NC / 2));
+        const C a = sm[fft_pad(e, PADSH)], b = sm[fft_pad(e + 1, PADSH)];
+        Vec16<T> o;
+        o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
+        st16(reinterpret_cast<T*>(blk) + 4 * v, o);
+    }
+}
+
+// filter tables in tile layout: F[adj][q][tile][ky][c] = S(ky,kx) * (adj ? conj(H) : H) / (2*Hp*Wp)
+template <typename T>
+__global__ void k_gd_tile_filter(const typename CxT<T>::type* __restrict__ H, const typename CxT<T>::type* __restrict__ Sy,
+                                 const typename CxT<T>::type* __restrict__ Sx, typename CxT<T>::type* __restrict__ F,
+                                 int DC, int Hp, int Wp, int Nh, int NTg) {
+    using C = typename CxT<T>::type;
+    const int64_t n = (int64_t)DC * NTg * Hp * LPC_GNC;
+    const T scale = (T)(0.5 / ((double)Hp * (double)Wp));
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % LPC_GNC);
+        int64_t r = i / LPC_GNC;
+        const int ky = (int)(r % Hp); r /= Hp;
+        const int tile = (int)(r % NTg);
+        const int q = (int)(r / NTg);
+        const int kx = tile * LPC_GNC + c;
+        C fwd, adj;
+        fwd.x = fwd.y = adj.x = adj.y = T(0);
+        if (kx < Nh) {
+            C hq = H[((int64_t)q * Hp + ky) * Nh + kx];
+            const C S = cx_mul(Sy[ky], Sx[kx]);
+            fwd = cx_mul(S, hq);
+            hq.y = -hq.y;
+            adj = cx_mul(S, hq);
+            fwd.x *= scale; fwd.y *= scale; adj.x *= scale; adj.y *= scale;
+        }
+        F[i] = fwd;
+        F[n + i] = adj;
+    }
+}
+
+}  // namespace lpc
