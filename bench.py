@@ -309,6 +309,13 @@ def main():
         "admm_cols(A)": 5.5 * Sp,                # v2: reads Tout(2Sp),H,R; writes Tin(2Sp)
         "update": 5.0 * d, "residual": 3.0 * d, "spec_mul_H": 3.0 * Sp, "spec_mul_Hadj": 3.0 * Sp,
     }
+    # fused GD engine: G-layout buffer (window rows only) and the filter table, per launch
+    Tg = 8.0 * Bg * (-(-(Wp // 2 + 1) // 4) * 4) * h * C
+    Fg = 8.0 * (-(-(Wp // 2 + 1) // 4) * 4) * Hp * C
+    kernel_bytes.update({
+        "gd_cols(H)": 2.0 * Tg + Fg, "gd_cols(Hadj)": 2.0 * Tg + Fg,
+        "gd_rows(residual)": 2.0 * Tg + d, "gd_rows(update)": 2.0 * Tg + 4.0 * d,
+    })
     own = {n: t for n, t in phases.items() if n in kernel_bytes}
     kname = max(own, key=own.get)  # our dominant kernel = the one with the longest launch
     kbytes = kernel_bytes[kname]
