@@ -82,8 +82,15 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
             }
         }
         C* dst = Tdst + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
+        if constexpr (sizeof(T) == 4 && NCT == 2) {
+            Vec32f o;  // one 32-byte store per chunk: (A[kx], A[kx+1], Xi[kx], Xi[kx+1])
+            o.v[0] = a[0].x; o.v[1] = a[0].y; o.v[2] = a[1].x; o.v[3] = a[1].y;
+            o.v[4] = x[0].x; o.v[5] = x[0].y; o.v[6] = x[1].x; o.v[7] = x[1].y;
+            st32(reinterpret_cast<float*>(dst), o);
+        } else {
 #pragma unroll
-        for (int c = 0; c < NCT; ++c) { dst[c] = a[c]; dst[NCT + c] = x[c]; }
+            for (int c = 0; c < NCT; ++c) { dst[c] = a[c]; dst[NCT + c] = x[c]; }
+        }
     }
     __syncthreads();
 }
@@ -110,27 +117,24 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     const C* src0 = Tin + (int64_t)p * NT * tile_stride + (int64_t)row * (2 * NCT);
     constexpr int IT = (NT + NTH - 1) / NTH;
     // all 32-byte chunks of the row in flight at once
-    Vec16<T> c0[IT], c1[IT];
+    static_assert(sizeof(T) == 4 && NCT == 2, "the fused engine is float-only with 32-byte chunks");
+    Vec32f ch[IT];
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
         const int t = tid + it * NTH;
-        if (t < NT) {
-            const T* s = reinterpret_cast<const T*>(src0 + (int64_t)t * tile_stride);
-            c0[it] = ld16_nc(s);
-            c1[it] = ld16_nc(s + 16 / sizeof(T));
-        }
+        if (t < NT) ch[it] = ld32_nc(reinterpret_cast<const float*>(src0 + (int64_t)t * tile_stride));
     }
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
         const int t = tid + it * NTH;
         if (t < NT) {
-            // c0 = (Vhat[kx], Vhat[kx+1]), c1 = (HVhat[kx], HVhat[kx+1])   (float: 2 complex per 16 B)
+            // chunk = (Vhat[kx], Vhat[kx+1], HVhat[kx], HVhat[kx+1])
 #pragma unroll
             for (int c = 0; c < NCT; ++c) {
                 const int kx = t * NCT + c;
                 C vh, hh;
-                vh.x = c0[it].v[2 * c]; vh.y = c0[it].v[2 * c + 1];
-                hh.x = c1[it].v[2 * c]; hh.y = c1[it].v[2 * c + 1];
+                vh.x = ch[it].v[2 * c]; vh.y = ch[it].v[2 * c + 1];
+                hh.x = ch[it].v[4 + 2 * c]; hh.y = ch[it].v[4 + 2 * c + 1];
                 if (kx < Nh) {
                     C y; y.x = vh.x - hh.y; y.y = vh.y + hh.x;
                     W[fft_pad(kx, PADSH)] = y;
@@ -151,8 +155,15 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     if constexpr (Wp % 4 == 0 && sizeof(T) == 4) {
         for (int q = tid; q < Wp / 4; q += NTH) {
             Vec16<T> a, b;
+            if constexpr (PADSH >= 30) {  // unpadded: two 16-byte shared loads instead of four 8-byte ones
+                const Vec16<T> lo = *reinterpret_cast<const Vec16<T>*>(W + 4 * q);
+                const Vec16<T> hi = *reinterpret_cast<const Vec16<T>*>(W + 4 * q + 2);
+                a.v[0] = lo.v[0]; b.v[0] = lo.v[1]; a.v[1] = lo.v[2]; b.v[1] = lo.v[3];
+                a.v[2] = hi.v[0]; b.v[2] = hi.v[1]; a.v[3] = hi.v[2]; b.v[3] = hi.v[3];
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { const C c = W[fft_pad(4 * q + e, PADSH)]; a.v[e] = c.x; b.v[e] = c.y; }
+                for (int e = 0; e < 4; ++e) { const C c = W[fft_pad(4 * q + e, PADSH)]; a.v[e] = c.x; b.v[e] = c.y; }
+            }
             st16(Vout + 4 * q, a);
             st16(HVout + 4 * q, b);
         }
@@ -246,7 +257,7 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                     if (row_in && j >= k.dcol0 && j < k.dcol0 + k.dpitch)
                         y = ld16_nc(dp + (int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0));
                     Vec16<T> t1, e1new, e0new, xin, rhon;
-                    T t0[4], t0d[4], dummy;
+                    T t0[4], t0d[4], dummy, av[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const T left = (e == 0) ? vl : vc.v[e - 1];
@@ -261,10 +272,17 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                         const bool inw = row_in && (jj >= k.sx) && (jj < k.sx + k.w);
                         point_update<T, true>(vc.v[e], hv.v[e], y.v[e], inw, xih.v[e], rhoh.v[e], k, xin.v[e], rhon.v[e]);
                         const T t1right = (e == 3) ? t1r : t1.v[e + 1];
-                        C z;
-                        z.x = -rhon.v[e] + ((t0d[e] - t0[e]) + (t1right - t1.v[e]));
-                        z.y = xin.v[e];
-                        W[fft_pad(jj, PADSH)] = z;
+                        av[e] = -rhon.v[e] + ((t0d[e] - t0[e]) + (t1right - t1.v[e]));
+                    }
+                    if constexpr (PADSH >= 30) {  // z = a + i*xi' for 4 pixels as two 16-byte shared stores
+                        Vec16<T> lo, hi;
+                        lo.v[0] = av[0]; lo.v[1] = xin.v[0]; lo.v[2] = av[1]; lo.v[3] = xin.v[1];
+                        hi.v[0] = av[2]; hi.v[1] = xin.v[2]; hi.v[2] = av[3]; hi.v[3] = xin.v[3];
+                        *reinterpret_cast<Vec16<T>*>(W + j) = lo;
+                        *reinterpret_cast<Vec16<T>*>(W + j + 2) = hi;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { C z; z.x = av[e]; z.y = xin.v[e]; W[fft_pad(j + e, PADSH)] = z; }
                     }
                     st16(xip + ro + j, xin);
                     st16(rhop + ro + j, rhon);

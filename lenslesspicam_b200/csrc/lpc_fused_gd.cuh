@@ -62,6 +62,7 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
     using C = typename CxT<T>::type;
     constexpr int NTH = LPC_ROWS_THREADS, NC = LPC_GNC, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
     constexpr int NTg = (Nh + NC - 1) / NC;
+    static_assert(sizeof(T) == 4 && NC == 4, "the fused engine is float-only with 32-byte chunks");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* W = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
@@ -77,10 +78,14 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
         for (int t = tid; t < NTg; t += NTH) {
             const C* sa = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC;
             C ya[NC], yb[NC];
+            {
+                const Vec32f va = ld32_nc(reinterpret_cast<const float*>(sa));  // one 32-byte load per (tile,row) chunk
+                Vec32f vb;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                ya[c] = sa[c];
-                if (has_b) yb[c] = sa[NC + c]; else { yb[c].x = T(0); yb[c].y = T(0); }
+                for (int e = 0; e < 8; ++e) vb.v[e] = 0.f;
+                if (has_b) vb = ld32_nc(reinterpret_cast<const float*>(sa + NC));
+#pragma unroll
+                for (int c = 0; c < NC; ++c) { ya[c].x = va.v[2 * c]; ya[c].y = va.v[2 * c + 1]; yb[c].x = vb.v[2 * c]; yb[c].y = vb.v[2 * c + 1]; }
             }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -165,11 +170,11 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
             }
         }
         C* da = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC;
+        Vec32f oa, ob;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            da[c] = a[c];
-            if (has_b) da[NC + c] = b[c];
-        }
+        for (int c = 0; c < NC; ++c) { oa.v[2 * c] = a[c].x; oa.v[2 * c + 1] = a[c].y; ob.v[2 * c] = b[c].x; ob.v[2 * c + 1] = b[c].y; }
+        st32(reinterpret_cast<float*>(da), oa);
+        if (has_b) st32(reinterpret_cast<float*>(da + NC), ob);
     }
 }
 

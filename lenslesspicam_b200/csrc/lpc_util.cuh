@@ -31,6 +31,23 @@ template <typename T> __device__ __forceinline__ void st16(T* p, const Vec16<T>&
     *reinterpret_cast<Vec16<T>*>(p) = x;
 }
 
+// 32-byte (256-bit) global accesses, sm_100+ (SASS LDG.E.256 / STG.E.256): one request per 32-byte
+// chunk of the T-/G-layout instead of two 16-byte ones -- the LSU data pipe, not HBM, bounds the
+// fused row kernels (profiles/r01_ncu_full_v2_three_kernels_raw.csv: 77-90 % wavefront utilisation).
+struct alignas(32) Vec32f { float v[8]; };
+__device__ __forceinline__ Vec32f ld32_nc(const float* p) {
+    Vec32f o;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(o.v[0]), "=f"(o.v[1]), "=f"(o.v[2]), "=f"(o.v[3]), "=f"(o.v[4]), "=f"(o.v[5]), "=f"(o.v[6]), "=f"(o.v[7])
+        : "l"(p));
+    return o;
+}
+__device__ __forceinline__ void st32(float* p, const Vec32f& x) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]),
+                 "f"(x.v[3]), "f"(x.v[4]), "f"(x.v[5]), "f"(x.v[6]), "f"(x.v[7])
+                 : "memory");
+}
+
 template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
 
