@@ -61,10 +61,11 @@ using IfftKern = void (*)(FusedK, const float2*, const float2*, float*);
 using FftKern = void (*)(FusedK, const float2*, const float*, float2*, float);
 using SpatKern = void (*)(FusedK, AdmmK<float>, const float2*, const float*, float2*, const float*, float*, float*,
                           const float*, float*);
-using ColsKern = void (*)(FusedK, const float2*, const float2*, float2*, const float2*, const float*, const float2*,
-                          const float2*);
-using GdRowsKern = void (*)(GdFusedK, const float2*, float2*, const float*, float*, float*, const float*, float, int);
-using GdColsKern = void (*)(GdFusedK, const float2*, float2*, const float2*);
+using ColsKern = void (*)(FusedK, const float2*, const float2*, const float2*, float2*, const float2*, const float*,
+                          const float2*, const float2*);
+using GdRowsKern = void (*)(GdFusedK, const float2*, const float2*, float2*, const float*, float*, float*, const float*,
+                            float, int);
+using GdColsKern = void (*)(GdFusedK, const float2*, const float2*, float2*, const float2*);
 struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; GdRowsKern gd[5]; };
 struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
@@ -165,6 +166,8 @@ struct Plan : lpc_plan_s {
     T* Rt = nullptr;        // Rn/2 in tile layout
     Cplx* tw_row = nullptr; // per-pass twiddle tables
     Cplx* tw_col = nullptr;
+    Cplx* tw_row_rev = nullptr;  // tables of the reversed radix sequences (the transform on the other side
+    Cplx* tw_col_rev = nullptr;  // of an in-register fused pass runs the reversed order)
     Cplx* spec1 = nullptr;  // [Np][splane], warm start only (lazily allocated)
     FftPlan plan_row{}, plan_col{};
     FusedK fk{};
@@ -337,6 +340,29 @@ struct Plan : lpc_plan_s {
         return LPC_OK;
     }
 
+    // twiddle tables of both menu sequences and of their reversed orders; shared-memory sizes cover both paddings
+    int upload_twiddles() {
+        int rc;
+        for (int which = 0; which < 4; ++which) {
+            const bool row = which < 2, rev = which & 1;
+            const int* rad = row ? rows_entry->radix : cols_entry->radix;
+            const int np = row ? rows_entry->npass : cols_entry->npass;
+            int seq[4];
+            for (int i = 0; i < np; ++i) seq[i] = rev ? rad[np - 1 - i] : rad[i];
+            FftPlan pl;
+            if (!make_fft_plan_from(row ? Wp : Hp, seq, np, &pl)) return fail(LPC_EINVAL, "make_fft_plan_from", "menu sequence");
+            std::vector<Cplx> tw;
+            fill_fft_twiddles(pl, &tw);
+            Cplx** dst = row ? (rev ? &tw_row_rev : &tw_row) : (rev ? &tw_col_rev : &tw_col);
+            if ((rc = alloc(dst, tw.size()))) return rc;
+            LPC_CK(cudaMemcpy(*dst, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+        }
+        return LPC_OK;
+    }
+    static size_t padded_bytes(int n_complex) {  // worst case of the two padding schemes (padsh 4 / none)
+        return (size_t)((fft_padded_len(n_complex, 4) + 1) & ~1) * sizeof(Cplx);
+    }
+
     // ---------------------------------------------------------------- engine v2 set-up
     const RowsEntry* rows_entry = nullptr;
     const ColsEntry* cols_entry = nullptr;
@@ -372,7 +398,7 @@ struct Plan : lpc_plan_s {
     int launch_cols(cudaStream_t st) {
         if constexpr (std::is_same<T, float>::value) {
             dim3 grid(fk.NT, Np);
-            cols_entry->kern[cols_variant]<<<grid, cols_variant ? 576 : 1024, smem_col, st>>>(fk, tw_col, Tout, Tin, Ht, Rt, Sy, Sx);
+            cols_entry->kern[cols_variant]<<<grid, cols_variant ? 576 : 1024, smem_col, st>>>(fk, tw_col, tw_col_rev, Tout, Tin, Ht, Rt, Sy, Sx);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -389,8 +415,8 @@ struct Plan : lpc_plan_s {
             if (!rows_entry || !cols_entry) return LPC_OK;
             if (!make_fft_plan_from(Wp, rows_entry->radix, rows_entry->npass, &plan_row)) return LPC_OK;
             if (!make_fft_plan_from(Hp, cols_entry->radix, cols_entry->npass, &plan_col)) return LPC_OK;
-            smem_row = (size_t)((fft_padded_len(Wp, plan_row.padsh) + 1) & ~1) * sizeof(Cplx);
-            smem_col = (size_t)fft_padded_len(2 * LPC_NCT * Hp, plan_col.padsh) * sizeof(Cplx);
+            smem_row = padded_bytes(Wp);
+            smem_col = padded_bytes(2 * LPC_NCT * Hp);
             int max_optin = 0;
             LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
             if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
@@ -411,13 +437,7 @@ struct Plan : lpc_plan_s {
             if ((rc = alloc(&Tout, tsz))) return rc;
             if ((rc = alloc(&Ht, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
             if ((rc = alloc(&Rt, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
-            std::vector<Cplx> tw;
-            fill_fft_twiddles(plan_row, &tw);
-            if ((rc = alloc(&tw_row, tw.size()))) return rc;
-            LPC_CK(cudaMemcpy(tw_row, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
-            fill_fft_twiddles(plan_col, &tw);
-            if ((rc = alloc(&tw_col, tw.size()))) return rc;
-            LPC_CK(cudaMemcpy(tw_col, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            if ((rc = upload_twiddles())) return rc;
             v2 = true;
             return LPC_OK;
         }
@@ -432,8 +452,8 @@ struct Plan : lpc_plan_s {
             if (!rows_entry || !cols_entry) return LPC_OK;
             if (!make_fft_plan_from(Wp, rows_entry->radix, rows_entry->npass, &plan_row)) return LPC_OK;
             if (!make_fft_plan_from(Hp, cols_entry->radix, cols_entry->npass, &plan_col)) return LPC_OK;
-            smem_row = (size_t)((fft_padded_len(Wp, plan_row.padsh) + 1) & ~1) * sizeof(Cplx);
-            smem_col = (size_t)fft_padded_len(LPC_GNC * Hp, plan_col.padsh) * sizeof(Cplx);
+            smem_row = padded_bytes(Wp);
+            smem_col = padded_bytes(LPC_GNC * Hp);
             int max_optin = 0;
             LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
             if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
@@ -446,13 +466,7 @@ struct Plan : lpc_plan_s {
             int rc;
             if ((rc = alloc(&Tg, (size_t)Np * gk.NTg * h * LPC_GNC))) return rc;
             if ((rc = alloc(&Fg, (size_t)2 * DC * gk.NTg * Hp * LPC_GNC))) return rc;
-            std::vector<Cplx> tw;
-            fill_fft_twiddles(plan_row, &tw);
-            if ((rc = alloc(&tw_row, tw.size()))) return rc;
-            LPC_CK(cudaMemcpy(tw_row, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
-            fill_fft_twiddles(plan_col, &tw);
-            if ((rc = alloc(&tw_col, tw.size()))) return rc;
-            LPC_CK(cudaMemcpy(tw_col, tw.data(), tw.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            if ((rc = upload_twiddles())) return rc;
             gd2 = true;
             return LPC_OK;
         }
@@ -461,7 +475,7 @@ struct Plan : lpc_plan_s {
         if constexpr (std::is_same<T, float>::value) {
             gk.Dd = Dd;
             dim3 grid((h + 1) / 2, Np);
-            rows_entry->gd[mode]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(gk, tw_row, Tg, data, xu, mom, consts, scalar, first);
+            rows_entry->gd[mode]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(gk, tw_row, tw_row_rev, Tg, data, xu, mom, consts, scalar, first);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -470,7 +484,7 @@ struct Plan : lpc_plan_s {
         if constexpr (std::is_same<T, float>::value) {
             dim3 grid(gk.NTg, Np);
             const Cplx* F = Fg + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
-            cols_entry->gd<<<grid, 576, smem_col, st>>>(gk, tw_col, Tg, F);
+            cols_entry->gd<<<grid, 576, smem_col, st>>>(gk, tw_col, tw_col_rev, Tg, F);
             LPC_KCHECK();
         }
         return LPC_OK;

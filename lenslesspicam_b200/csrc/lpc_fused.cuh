@@ -45,9 +45,10 @@ constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIAN
 #define LPC_ROW_MENU(X) \
     X(3840, 15, 16, 16) X(2048, 16, 16, 8) X(1024, 16, 16, 4) X(512, 16, 8, 4) X(480, 15, 16, 2) \
     X(288, 9, 16, 2) X(125, 5, 5, 5) X(75, 15, 5) X(64, 16, 4) X(54, 9, 6)
+// (column sequences end in a small radix: that pass is fused with the spectral update in registers)
 #define LPC_COL_MENU(X) \
-    X(2160, 15, 16, 9) X(1536, 12, 16, 8) X(768, 3, 16, 16) X(384, 3, 16, 8) X(405, 15, 9, 3) \
-    X(270, 15, 9, 2) X(200, 5, 8, 5) X(48, 3, 16) X(45, 15, 3) X(40, 5, 8) X(27, 9, 3)
+    X(2160, 15, 16, 9) X(1536, 12, 16, 8) X(768, 16, 16, 3) X(384, 16, 8, 3) X(405, 15, 9, 3) \
+    X(270, 15, 9, 2) X(200, 5, 8, 5) X(48, 16, 3) X(45, 15, 3) X(40, 5, 8) X(27, 9, 3)
 
 struct FusedK {
     int Hp, Wp, Nh, NT;  // NT tiles of LPC_NCT columns cover Nh = Wp/2+1
@@ -148,27 +149,24 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
         }
     }
     __syncthreads();
-    CtaFftStatic<T, SEQ, +1, 1, NTH>::run(W, tw, tid);
+    // all passes but the last in shared memory; the last pass leaves pixel j + m*(Wp/RL) of the row in
+    // register m of butterfly j, which goes straight to HBM (coalesced 4-byte stores per m): no
+    // shared-memory round trip and no barrier for the output
+    using TR = SeqTraits<SEQ>;
+    TR::template run_butlast<T, +1, 1, NTH>(W, tw, tid);
+    constexpr int RL = TR::last, NSL = TR::ns_last;
     const int64_t plane = (int64_t)Hp * Wp;
     T* Vout = VH + (int64_t)p * plane + (int64_t)row * Wp;
     T* HVout = Vout + (int64_t)f.n_planes * plane;
-    if constexpr (Wp % 4 == 0 && sizeof(T) == 4) {
-        for (int q = tid; q < Wp / 4; q += NTH) {
-            Vec16<T> a, b;
-            if constexpr (PADSH >= 30) {  // unpadded: two 16-byte shared loads instead of four 8-byte ones
-                const Vec16<T> lo = *reinterpret_cast<const Vec16<T>*>(W + 4 * q);
-                const Vec16<T> hi = *reinterpret_cast<const Vec16<T>*>(W + 4 * q + 2);
-                a.v[0] = lo.v[0]; b.v[0] = lo.v[1]; a.v[1] = lo.v[2]; b.v[1] = lo.v[3];
-                a.v[2] = hi.v[0]; b.v[2] = hi.v[1]; a.v[3] = hi.v[2]; b.v[3] = hi.v[3];
-            } else {
+    for (int j = tid; j < NSL; j += NTH) {
+        C v[RL];
+        fft_bfly_load<T, RL>(W, 0, 1, PADSH, Wp, j, v);
+        fft_bfly_compute<T, RL, +1>(v, tw + TR::tw_off_last, NSL, j);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { const C c = W[fft_pad(4 * q + e, PADSH)]; a.v[e] = c.x; b.v[e] = c.y; }
-            }
-            st16(Vout + 4 * q, a);
-            st16(HVout + 4 * q, b);
+        for (int m = 0; m < RL; ++m) {
+            Vout[j + m * NSL] = v[m].x;
+            HVout[j + m * NSL] = v[m].y;
         }
-    } else {
-        for (int j = tid; j < Wp; j += NTH) { const C c = W[fft_pad(j, PADSH)]; Vout[j] = c.x; HVout[j] = c.y; }
     }
 }
 
@@ -323,21 +321,27 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
 // ---------------------------------------------------------------------------------------------
 // A: one CTA owns one tile: LPC_NCT columns x 2 slots = 4 interleaved column transforms of
 // length Hp, resident in shared memory from the load to the store.
-//     forward column FFT of (2A_row, 2Xi_row)
+//     forward column FFT of (2A_row, 2Xi_row)      radix sequence SEQ
 //     Vhat  = Rn * (A - S*conj(H)*Xi)        HVhat = S*H*Vhat        (Rn carries 1/(2*Hp*Wp))
-//     inverse column FFT -> row spectra of (V, HV)/Wp
+//     inverse column FFT -> row spectra of (V, HV)/Wp      radix sequence REVERSED
+// The last forward pass, the spectral update and the first inverse pass happen in registers: with
+// the reversed sequence the first inverse butterfly j reads exactly the bins j + m*(Hp/RL) that the
+// last forward butterfly j produced, and a thread takes both slots of its column, so the coupled
+// update is thread-local.  Saves 4 of the 16 shared-memory sweeps of the tile and 3 barriers.
 // Ht: [DC][NT][Hp][NCT] complex, Rt: same shape real (tile layout, built once per PSF).
-// grid (NT, planes)
+// twF / twI: twiddle tables of SEQ / of the reversed sequence.           grid (NT, planes)
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename SEQ, int NTH, int MINB>
 __global__ void __launch_bounds__(NTH, MINB)
-k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typename CxT<T>::type* __restrict__ Tsrc,
-            typename CxT<T>::type* __restrict__ Tdst, const typename CxT<T>::type* __restrict__ Ht,
-            const T* __restrict__ Rt, const typename CxT<T>::type* __restrict__ Sy,
-            const typename CxT<T>::type* __restrict__ Sx) {
+k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ twF, const typename CxT<T>::type* __restrict__ twI,
+            const typename CxT<T>::type* __restrict__ Tsrc, typename CxT<T>::type* __restrict__ Tdst,
+            const typename CxT<T>::type* __restrict__ Ht, const T* __restrict__ Rt,
+            const typename CxT<T>::type* __restrict__ Sy, const typename CxT<T>::type* __restrict__ Sx) {
     using C = typename CxT<T>::type;
+    using TR = SeqTraits<SEQ>;
+    using REV = typename TR::Rev;
     constexpr int NCT = LPC_NCT, NB = 2 * NCT;
-    constexpr int Hp = SEQ::N, PADSH = SEQ::padsh;
+    constexpr int Hp = SEQ::N, PF = SEQ::padsh, PI = REV::padsh, RL = TR::last, NSL = TR::ns_last;
     constexpr int n = Hp * NB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* sm = reinterpret_cast<C*>(smem_raw);
@@ -348,13 +352,12 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     const int q = p % f.DC;
     const C* src = Tsrc + ((int64_t)p * NT + tile) * n;
     C* dst = Tdst + ((int64_t)p * NT + tile) * n;
-
     const C* Hq = Ht + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
     const T* Rq = Rt + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
     // the tile is one contiguous block: 16-byte loads, all of a thread's loads in flight before the
     // first shared-memory store; H and R (needed after the forward FFT) are pulled into L2 meanwhile
     {
-        constexpr int NV = n / 2;                       // 16-byte vectors (2 complex) in the tile
+        constexpr int NV = n / 2;  // 16-byte vectors (2 complex) in the tile
         constexpr int IT = (NV + NTH - 1) / NTH;
         Vec16<T> buf[IT];
 #pragma unroll
@@ -362,7 +365,7 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
             const int v = tid + it * NTH;
             if (v < NV) buf[it] = ld16_nc(reinterpret_cast<const T*>(src) + 4 * v);
         }
-        for (int e = tid * 16; e < Hp * NCT; e += NTH * 16) {   // one prefetch per 128-byte line of H, per 64 B of R
+        for (int e = tid * 16; e < Hp * NCT; e += NTH * 16) {  // one prefetch per 128-byte line of H, per 64 B of R
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Hq + e));
             if ((e & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(Rq + e));
         }
@@ -372,36 +375,62 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
             if (v < NV) {
                 C a, b;
                 a.x = buf[it].v[0]; a.y = buf[it].v[1]; b.x = buf[it].v[2]; b.y = buf[it].v[3];
-                sm[fft_pad(2 * v, PADSH)] = a;
-                sm[fft_pad(2 * v + 1, PADSH)] = b;
+                sm[fft_pad(2 * v, PF)] = a;
+                sm[fft_pad(2 * v + 1, PF)] = b;
             }
         }
     }
     __syncthreads();
-    CtaFftStatic<T, SEQ, -1, NB, NTH>::run(sm, tw, tid);
+    TR::template run_butlast<T, -1, NB, NTH>(sm, twF, tid);
 
-#pragma unroll 2
-    for (int e = tid; e < Hp * NCT; e += NTH) {
-        const int ky = e / NCT, c = e - ky * NCT;
-        const int kx = tile * NCT + c;
-        const int ia = fft_pad(ky * NB + c, PADSH), ix = fft_pad(ky * NB + NCT + c, PADSH);
-        const C A = sm[ia];
-        const C Xi = sm[ix];
-        const C Hh = __ldg(Hq + e);
-        const T Rn = __ldg(Rq + e);
-        const C S = cx_mul(__ldg(Sy + ky), __ldg(Sx + (kx < f.Nh ? kx : 0)));
-        const C Hs = cx_mul(S, Hh);
-        C Hc = Hh; Hc.y = -Hc.y;
-        const C Hsa = cx_mul(S, Hc);
-        const C m = cx_mul(Hsa, Xi);
-        C Vh; Vh.x = Rn * (A.x - m.x); Vh.y = Rn * (A.y - m.y);
-        sm[ia] = Vh;
-        sm[ix] = cx_mul(Hs, Vh);
+    // ---- last forward pass + spectral update + first inverse pass, in registers
+    constexpr int totalp = NSL * NCT;  // (column, butterfly) pairs; a thread owns both slots of its column
+    constexpr int MAXP = (totalp + NTH - 1) / NTH;
+    C v0[MAXP][RL], v1[MAXP][RL];
+#pragma unroll
+    for (int it = 0; it < MAXP; ++it) {
+        const int g = tid + it * NTH;
+        if (MAXP * NTH == totalp || g < totalp) {
+            const int c = g % NCT, j = g / NCT;
+            fft_bfly_load<T, RL>(sm, c, NB, PF, Hp, j, v0[it]);
+            fft_bfly_load<T, RL>(sm, NCT + c, NB, PF, Hp, j, v1[it]);
+            fft_bfly_compute<T, RL, -1>(v0[it], twF + TR::tw_off_last, NSL, j);
+            fft_bfly_compute<T, RL, -1>(v1[it], twF + TR::tw_off_last, NSL, j);
+            const int kx = tile * NCT + c;
+            const C sxv = __ldg(Sx + (kx < f.Nh ? kx : 0));
+#pragma unroll
+            for (int m = 0; m < RL; ++m) {
+                const int ky = j + m * NSL;
+                const int e = ky * NCT + c;
+                const C Hh = __ldg(Hq + e);
+                const T Rn = __ldg(Rq + e);
+                const C S = cx_mul(__ldg(Sy + ky), sxv);
+                const C Hs = cx_mul(S, Hh);
+                C Hc = Hh; Hc.y = -Hc.y;
+                const C Hsa = cx_mul(S, Hc);
+                const C mm = cx_mul(Hsa, v1[it][m]);
+                C Vh; Vh.x = Rn * (v0[it][m].x - mm.x); Vh.y = Rn * (v0[it][m].y - mm.y);
+                v0[it][m] = Vh;
+                v1[it][m] = cx_mul(Hs, Vh);
+            }
+            Dft<T, RL, +1>::run(v0[it]);  // first pass of the reversed sequence: Ns = 1, no twiddles
+            Dft<T, RL, +1>::run(v1[it]);
+        }
     }
     __syncthreads();
-    CtaFftStatic<T, SEQ, +1, NB, NTH>::run(sm, tw, tid);
+#pragma unroll
+    for (int it = 0; it < MAXP; ++it) {
+        const int g = tid + it * NTH;
+        if (MAXP * NTH == totalp || g < totalp) {
+            const int c = g % NCT, j = g / NCT;
+            fft_bfly_store<T, RL>(sm, c, NB, PI, 1, j, v0[it]);
+            fft_bfly_store<T, RL>(sm, NCT + c, NB, PI, 1, j, v1[it]);
+        }
+    }
+    __syncthreads();
+    SeqTraits<REV>::template run_butfirst<T, +1, NB, NTH>(sm, twI, tid);
     for (int v = tid; v < n / 2; v += NTH) {
-        const C a = sm[fft_pad(2 * v, PADSH)], b = sm[fft_pad(2 * v + 1, PADSH)];
+        const C a = sm[fft_pad(2 * v, PI)], b = sm[fft_pad(2 * v + 1, PI)];
         Vec16<T> o;
         o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
         st16(reinterpret_cast<T*>(dst) + 4 * v, o);

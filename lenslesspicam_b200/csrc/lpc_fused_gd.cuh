@@ -53,14 +53,21 @@ __device__ __forceinline__ int gdf_data_plane(int p, const GdFusedK& k) {
 //   scalar: Nesterov mu (gd.py:183-188) or FISTA beta = (t_k - 1)/t_{k+1} (gd.py:238-239)
 //   first : FISTA only -- right after reset() the reference's previous iterate aliases the stepped
 //           estimate (gd.py:233,236), mirrored
+// The inverse transform runs SEQ, the forward one the REVERSED sequence, so that the last inverse
+// pass, the element-wise stage and the first forward pass share registers: butterfly j holds pixels
+// j + m*(Wp/RL), m < RL (coalesced 4-byte accesses to x / mom / y per m).
+// twI: tables of SEQ (inverse), twF: tables of the reversed sequence (forward).
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename SEQ, int MODE>
 __global__ void __launch_bounds__(LPC_ROWS_THREADS, 4)
-k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT<T>::type* __restrict__ Tg,
-          const T* __restrict__ data, T* __restrict__ x, T* __restrict__ mom, const T* __restrict__ consts, T scalar,
-          int first) {
+k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typename CxT<T>::type* __restrict__ twF,
+          typename CxT<T>::type* __restrict__ Tg, const T* __restrict__ data, T* __restrict__ x, T* __restrict__ mom,
+          const T* __restrict__ consts, T scalar, int first) {
     using C = typename CxT<T>::type;
-    constexpr int NTH = LPC_ROWS_THREADS, NC = LPC_GNC, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
+    using TR = SeqTraits<SEQ>;
+    using REV = typename TR::Rev;
+    constexpr int NTH = LPC_ROWS_THREADS, NC = LPC_GNC, Wp = SEQ::N, Nh = Wp / 2 + 1;
+    constexpr int PI = SEQ::padsh, PF = REV::padsh, RL = TR::last, NSL = TR::ns_last;
     constexpr int NTg = (Nh + NC - 1) / NC;
     static_assert(sizeof(T) == 4 && NC == 4, "the fused engine is float-only with 32-byte chunks");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -74,7 +81,7 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
     C* Tp = Tg + (int64_t)p * NTg * tile_stride;
 
     if (MODE != LPC_GD_INIT) {
-        // gather the two half-spectrum rows, build the full-length packed row Y_a + i*Y_b, inverse FFT
+        // gather the two half-spectrum rows, build the full-length packed row Y_a + i*Y_b
         for (int t = tid; t < NTg; t += NTH) {
             const C* sa = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC;
             C ya[NC], yb[NC];
@@ -92,70 +99,87 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
                 const int kx = t * NC + c;
                 if (kx < Nh) {
                     C y; y.x = ya[c].x - yb[c].y; y.y = ya[c].y + yb[c].x;
-                    W[fft_pad(kx, PADSH)] = y;
+                    W[fft_pad(kx, PI)] = y;
                     const int m = Wp - kx;
                     if (kx >= 1 && m >= Nh) {
                         C ym; ym.x = ya[c].x + yb[c].y; ym.y = yb[c].x - ya[c].y;
-                        W[fft_pad(m, PADSH)] = ym;
+                        W[fft_pad(m, PI)] = ym;
                     }
                 }
             }
         }
         __syncthreads();
-        CtaFftStatic<T, SEQ, +1, 1, NTH>::run(W, tw, tid);
+        TR::template run_butlast<T, +1, 1, NTH>(W, twI, tid);  // inverse FFT, all passes but the last
     }
 
-    // element-wise stage on the window columns; everything outside the window becomes the zero padding
+    // ---- last inverse pass -> element-wise stage -> first forward pass, in registers
     const int64_t ia = ((int64_t)p * h + ra) * w, ib = ia + w;
     const T alpha = (MODE >= LPC_GD_UPD_GD) ? consts[3 * f.C + p % f.C] : T(0);
     const T* dpl = data + (int64_t)gdf_data_plane(p, f) * h * w;
-    for (int j = tid; j < Wp; j += NTH) {
-        C z; z.x = T(0); z.y = T(0);
-        const int col = j - sx;
-        if (col >= 0 && col < w) {
-            if (MODE == LPC_GD_INIT) {
-                z.x = x[ia + col];
-                if (has_b) z.y = x[ib + col];
-            } else {
-                const C g = W[fft_pad(j, PADSH)];
-                if (MODE == LPC_GD_RESID) {
-                    z.x = g.x - dpl[(int64_t)ra * w + col];          // crop(Hx) - y   (gd.py:129)
-                    if (has_b) z.y = g.y - dpl[(int64_t)rb * w + col];
-                } else {
+    constexpr int MAXB = (NSL + NTH - 1) / NTH;
+    C v[MAXB][RL];
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        if (s == 1 && !has_b) break;
-                        const int64_t o = (s == 0 ? ia : ib) + col;
-                        const T gs = (s == 0) ? g.x : g.y;
-                        T xn;
-                        if (MODE == LPC_GD_UPD_GD) {                  // gd.py:132-134
-                            const T v = x[o] - alpha * gs;
-                            xn = v > T(0) ? v : T(0);
-                        } else if (MODE == LPC_GD_UPD_NESTEROV) {     // gd.py:183-188
-                            const T p_prev = mom[o];
-                            const T p_new = scalar * p_prev - alpha * gs;
-                            mom[o] = p_new;
-                            const T v = x[o] + (-scalar * p_prev + (T(1) + scalar) * p_new);
-                            xn = v > T(0) ? v : T(0);
-                        } else {                                       // FISTA, gd.py:235-241
-                            const T zz = x[o] - alpha * gs;
-                            const T xk = zz > T(0) ? zz : T(0);
-                            const T prev = first ? zz : mom[o];
-                            mom[o] = xk;
-                            xn = xk + scalar * (xk - prev);
+    for (int it = 0; it < MAXB; ++it) {
+        const int j = tid + it * NTH;
+        if (MAXB * NTH == NSL || j < NSL) {
+            if (MODE != LPC_GD_INIT) {
+                fft_bfly_load<T, RL>(W, 0, 1, PI, Wp, j, v[it]);
+                fft_bfly_compute<T, RL, +1>(v[it], twI + TR::tw_off_last, NSL, j);
+            }
+#pragma unroll
+            for (int m = 0; m < RL; ++m) {
+                const int col = j + m * NSL - sx;  // window column of padded pixel j + m*NSL
+                C z; z.x = T(0); z.y = T(0);       // everything outside the window is the zero padding
+                if (col >= 0 && col < w) {
+                    if (MODE == LPC_GD_INIT) {
+                        z.x = x[ia + col];
+                        if (has_b) z.y = x[ib + col];
+                    } else if (MODE == LPC_GD_RESID) {
+                        z.x = v[it][m].x - dpl[(int64_t)ra * w + col];  // crop(Hx) - y   (gd.py:129)
+                        if (has_b) z.y = v[it][m].y - dpl[(int64_t)rb * w + col];
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            if (s == 1 && !has_b) break;
+                            const int64_t o = (s == 0 ? ia : ib) + col;
+                            const T gs = (s == 0) ? v[it][m].x : v[it][m].y;
+                            T xn;
+                            if (MODE == LPC_GD_UPD_GD) {  // gd.py:132-134
+                                const T u = x[o] - alpha * gs;
+                                xn = u > T(0) ? u : T(0);
+                            } else if (MODE == LPC_GD_UPD_NESTEROV) {  // gd.py:183-188
+                                const T p_prev = mom[o];
+                                const T p_new = scalar * p_prev - alpha * gs;
+                                mom[o] = p_new;
+                                const T u = x[o] + (-scalar * p_prev + (T(1) + scalar) * p_new);
+                                xn = u > T(0) ? u : T(0);
+                            } else {  // FISTA, gd.py:235-241
+                                const T zz = x[o] - alpha * gs;
+                                const T xk = zz > T(0) ? zz : T(0);
+                                const T prev = first ? zz : mom[o];
+                                mom[o] = xk;
+                                xn = xk + scalar * (xk - prev);
+                            }
+                            x[o] = xn;
+                            if (s == 0) z.x = xn; else z.y = xn;
                         }
-                        x[o] = xn;
-                        if (s == 0) z.x = xn; else z.y = xn;
                     }
                 }
+                v[it][m] = z;
             }
+            Dft<T, RL, -1>::run(v[it]);  // first pass of the reversed sequence: Ns = 1, no twiddles
         }
-        W[fft_pad(j, PADSH)] = z;
     }
     __syncthreads();
+#pragma unroll
+    for (int it = 0; it < MAXB; ++it) {
+        const int j = tid + it * NTH;
+        if (MAXB * NTH == NSL || j < NSL) fft_bfly_store<T, RL>(W, 0, 1, PF, 1, j, v[it]);
+    }
+    __syncthreads();
+    SeqTraits<REV>::template run_butfirst<T, -1, 1, NTH>(W, twF, tid);
 
-    // forward FFT of the packed pair, separate, store the two half-spectrum rows (no 1/2: folded into the filter)
-    CtaFftStatic<T, SEQ, -1, 1, NTH>::run(W, tw, tid);
+    // separate the packed pair and store the two half-spectrum rows (no 1/2: folded into the filter)
     for (int t = tid; t < NTg; t += NTH) {
         C a[NC], b[NC];
 #pragma unroll
@@ -163,8 +187,8 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
             const int kx = t * NC + c;
             a[c].x = a[c].y = b[c].x = b[c].y = T(0);
             if (kx < Nh) {
-                const C zk = W[fft_pad(kx, PADSH)];
-                const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PADSH)];
+                const C zk = W[fft_pad(kx, PF)];
+                const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PF)];
                 a[c].x = zk.x + zm.x; a[c].y = zk.y - zm.y;   // Z[k] + conj(Z[-k])
                 b[c].x = zk.y + zm.y; b[c].y = zm.x - zk.x;   // (Z[k] - conj(Z[-k])) / i
             }
@@ -182,13 +206,17 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
 // columns: one CTA per tile of LPC_GNC columns, in place.   grid (NTg, planes)
 //   F: filter in tile layout [DC][NTg][Hp][4] = S*H/(2*Hp*Wp) (convolve) or S*conj(H)/(2*Hp*Wp)
 //   (deconvolve; the same shift S, rfft_convolve.py:195)
+//   forward FFT with SEQ, inverse with the reversed sequence; the last forward pass, the filter
+//   multiply and the first inverse pass share registers (see k_admm_cols).
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename SEQ, int NTH, int MINB>
 __global__ void __launch_bounds__(NTH, MINB)
-k_gd_cols(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT<T>::type* __restrict__ Tg,
-          const typename CxT<T>::type* __restrict__ F) {
+k_gd_cols(GdFusedK f, const typename CxT<T>::type* __restrict__ twF, const typename CxT<T>::type* __restrict__ twI,
+          typename CxT<T>::type* __restrict__ Tg, const typename CxT<T>::type* __restrict__ F) {
     using C = typename CxT<T>::type;
-    constexpr int NC = LPC_GNC, Hp = SEQ::N, PADSH = SEQ::padsh;
+    using TR = SeqTraits<SEQ>;
+    using REV = typename TR::Rev;
+    constexpr int NC = LPC_GNC, Hp = SEQ::N, PF = SEQ::padsh, PI = REV::padsh, RL = TR::last, NSL = TR::ns_last;
     constexpr int n = Hp * NC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* sm = reinterpret_cast<C*>(smem_raw);
@@ -210,23 +238,41 @@ k_gd_cols(GdFusedK f, const typename CxT<T>::type* __restrict__ tw, typename CxT
             const Vec16<T> d = ld16_nc(reinterpret_cast<const T*>(blk) + 4 * (v - sy * (NC / 2)));
             a.x = d.v[0]; a.y = d.v[1]; b.x = d.v[2]; b.y = d.v[3];
         }
-        sm[fft_pad(2 * v, PADSH)] = a;
-        sm[fft_pad(2 * v + 1, PADSH)] = b;
+        sm[fft_pad(2 * v, PF)] = a;
+        sm[fft_pad(2 * v + 1, PF)] = b;
     }
     __syncthreads();
-    CtaFftStatic<T, SEQ, -1, NC, NTH>::run(sm, tw, tid);
-    for (int e = tid; e < n; e += NTH) {
-        const int i = fft_pad(e, PADSH);
-        sm[i] = cx_mul(sm[i], __ldg(Fq + e));
+    TR::template run_butlast<T, -1, NC, NTH>(sm, twF, tid);
+
+    constexpr int total = NSL * NC;
+    constexpr int MAXB = (total + NTH - 1) / NTH;
+    C v[MAXB][RL];
+#pragma unroll
+    for (int it = 0; it < MAXB; ++it) {
+        const int g = tid + it * NTH;
+        if (MAXB * NTH == total || g < total) {
+            const int c = g % NC, j = g / NC;
+            fft_bfly_load<T, RL>(sm, c, NC, PF, Hp, j, v[it]);
+            fft_bfly_compute<T, RL, -1>(v[it], twF + TR::tw_off_last, NSL, j);
+#pragma unroll
+            for (int m = 0; m < RL; ++m) v[it][m] = cx_mul(v[it][m], __ldg(Fq + (j + m * NSL) * NC + c));
+            Dft<T, RL, +1>::run(v[it]);
+        }
     }
     __syncthreads();
-    CtaFftStatic<T, SEQ, +1, NC, NTH>::run(sm, tw, tid);
-    for (int v = tid; v < h * (NC / 2); v += NTH) {
-        const int e = 2 * (v + sy * (NC / 2));
-        const C a = sm[fft_pad(e, PADSH)], b = sm[fft_pad(e + 1, PADSH)];
+#pragma unroll
+    for (int it = 0; it < MAXB; ++it) {
+        const int g = tid + it * NTH;
+        if (MAXB * NTH == total || g < total) fft_bfly_store<T, RL>(sm, g % NC, NC, PI, 1, g / NC, v[it]);
+    }
+    __syncthreads();
+    SeqTraits<REV>::template run_butfirst<T, +1, NC, NTH>(sm, twI, tid);
+    for (int v2 = tid; v2 < h * (NC / 2); v2 += NTH) {
+        const int e = 2 * (v2 + sy * (NC / 2));
+        const C a = sm[fft_pad(e, PI)], b = sm[fft_pad(e + 1, PI)];
         Vec16<T> o;
         o.v[0] = a.x; o.v[1] = a.y; o.v[2] = b.x; o.v[3] = b.y;
-        st16(reinterpret_cast<T*>(blk) + 4 * v, o);
+        st16(reinterpret_cast<T*>(blk) + 4 * v2, o);
     }
 }
 
