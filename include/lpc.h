@@ -73,8 +73,7 @@ extern "C" {
 /* lpc_plan_create flags */
 #define LPC_FLAG_NONE 0
 #define LPC_FLAG_NO_GRAPH 1   /* never capture the iteration loop in a CUDA graph        */
-#define LPC_FLAG_LITERAL 2    /* debug: reference's literal 6-FFT ADMM order (bisecting) */
-#define LPC_FLAG_ENGINE_V1 4  /* ADMM: K1/K2 + cuFFT engine instead of the fused own-FFT engine  */
+#define LPC_FLAG_ENGINE_V1 4  /* K1/K2/K3 + cuFFT engine instead of the fused own-FFT engine (A/B, bisecting) */
 
 typedef struct lpc_plan_s* lpc_plan_t;
 

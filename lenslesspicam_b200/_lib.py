@@ -19,7 +19,7 @@ ALGO_CONV, ALGO_ADMM, ALGO_GD, ALGO_NESTEROV, ALGO_FISTA = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 NORMS = {"backward": 0, "ortho": 1, "forward": 2}
 STATE_IMAGE_EST, STATE_FORWARD, STATE_XI, STATE_RHO, STATE_ETA0, STATE_ETA1 = range(6)
-FLAG_NONE, FLAG_NO_GRAPH, FLAG_LITERAL, FLAG_ENGINE_V1 = 0, 1, 2, 4
+FLAG_NONE, FLAG_NO_GRAPH, FLAG_ENGINE_V1 = 0, 1, 4
 
 _lock = threading.Lock()
 _lib = None

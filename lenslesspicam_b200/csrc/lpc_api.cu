@@ -179,6 +179,11 @@ struct Plan : lpc_plan_s {
     Cplx* Fg = nullptr;     // [2][DC][NTg][Hp][4]: S*H/(2N) and S*conj(H)/(2N)
     T* xu = nullptr;        // [Np][h][w] image estimate, unpadded planar
     GdFusedK gk{};
+    // independent planes run as concurrent chains on side streams (forked / joined inside lpc_run)
+    static constexpr int MAX_CHAINS = 4;
+    int n_chains = 1;
+    cudaStream_t side[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHAINS] = {nullptr, nullptr, nullptr, nullptr};
     // ---- cuFFT
     cufftHandle fwd_psf = 0, fwd = 0, inv = 0, fwd1 = 0, inv1 = 0;
     bool have_fwd_psf = false, have_fwd = false, have_inv = false, have_1 = false;
@@ -197,6 +202,8 @@ struct Plan : lpc_plan_s {
     ~Plan() override {
         cudaSetDevice(device);
         drop_graph();
+        for (int i = 0; i < MAX_CHAINS; ++i) { if (side[i]) cudaStreamDestroy(side[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
         if (have_fwd_psf) cufftDestroy(fwd_psf);
         if (have_fwd) cufftDestroy(fwd);
         if (have_inv) cufftDestroy(inv);
@@ -332,6 +339,19 @@ struct Plan : lpc_plan_s {
             if ((rc = make_fft(&inv, &have_inv, FftTraits<T>::C2R, nb))) return rc;
         }
         if ((rc = bind_work())) return rc;
+        if (v2 || gd2) {
+            int want = 3;
+            if (const char* e = getenv("LPC_CHAINS")) want = atoi(e);
+            if (want > MAX_CHAINS) want = MAX_CHAINS;
+            if (want > Np) want = Np;
+            if (want < 1) want = 1;
+            n_chains = want;
+            LPC_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            for (int i = 1; i < n_chains; ++i) {
+                LPC_CK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+                LPC_CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+            }
+        }
         // shift tables do not depend on the PSF
         k_shift_table<T><<<(Hp + 127) / 128, 128>>>(Sy, Hp, Hp);
         k_shift_table<T><<<(Nh + 127) / 128, 128>>>(Sx, Nh, Wp);
@@ -369,10 +389,12 @@ struct Plan : lpc_plan_s {
     int ry_log2 = 0;       // B2 processes 1 << ry_log2 rows per CTA (measured: 1 row 315 us, 2 rows 400, 4 rows 465)
     int cols_variant = 1;  // A: 0 = 1024 threads x 1 CTA/SM, 1 = 576 threads x 2 CTAs/SM
 
-    int launch_rows_ifft(cudaStream_t st) {
+    int launch_rows_ifft(cudaStream_t st, int p0 = 0, int np = -1) {
         if constexpr (std::is_same<T, float>::value) {
-            dim3 grid(Hp, Np);
-            rows_entry->ifft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, tw_row, Tin, VH);
+            if (np < 0) np = Np;
+            dim3 grid(Hp, np);
+            FusedK k = fk; k.plane0 = p0;
+            rows_entry->ifft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, Tin, VH);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -385,20 +407,24 @@ struct Plan : lpc_plan_s {
         }
         return LPC_OK;
     }
-    int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o) {
+    int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o, int p0 = 0, int np = -1) {
         if constexpr (std::is_same<T, float>::value) {
+            if (np < 0) np = Np;
             const int ry = 1 << ry_log2;
-            dim3 grid((Hp + ry - 1) / ry, Np);
-            rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(fk, admm_k(), tw_row, VH, Tout, data,
+            dim3 grid((Hp + ry - 1) / ry, np);
+            FusedK k = fk; k.plane0 = p0;
+            rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, admm_k(), tw_row, VH, Tout, data,
                                                                           AX + (int64_t)Np * plane, rho, eta_i, eta_o);
             LPC_KCHECK();
         }
         return LPC_OK;
     }
-    int launch_cols(cudaStream_t st) {
+    int launch_cols(cudaStream_t st, int p0 = 0, int np = -1) {
         if constexpr (std::is_same<T, float>::value) {
-            dim3 grid(fk.NT, Np);
-            cols_entry->kern[cols_variant]<<<grid, cols_variant ? 576 : 1024, smem_col, st>>>(fk, tw_col, tw_col_rev, Tout, Tin, Ht, Rt, Sy, Sx);
+            if (np < 0) np = Np;
+            dim3 grid(fk.NT, np);
+            FusedK k = fk; k.plane0 = p0;
+            cols_entry->kern[cols_variant]<<<grid, cols_variant ? 576 : 1024, smem_col, st>>>(k, tw_col, tw_col_rev, Tout, Tin, Ht, Rt, Sy, Sx);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -471,20 +497,24 @@ struct Plan : lpc_plan_s {
             return LPC_OK;
         }
     }
-    int gd2_rows(int mode, T scalar, int first, cudaStream_t st) {
+    int gd2_rows(int mode, T scalar, int first, cudaStream_t st, int p0 = 0, int np = -1) {
         if constexpr (std::is_same<T, float>::value) {
             gk.Dd = Dd;
-            dim3 grid((h + 1) / 2, Np);
-            rows_entry->gd[mode]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(gk, tw_row, tw_row_rev, Tg, data, xu, mom, consts, scalar, first);
+            if (np < 0) np = Np;
+            dim3 grid((h + 1) / 2, np);
+            GdFusedK k = gk; k.plane0 = p0;
+            rows_entry->gd[mode]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, tw_row_rev, Tg, data, xu, mom, consts, scalar, first);
             LPC_KCHECK();
         }
         return LPC_OK;
     }
-    int gd2_cols(int adjoint, cudaStream_t st) {
+    int gd2_cols(int adjoint, cudaStream_t st, int p0 = 0, int np = -1) {
         if constexpr (std::is_same<T, float>::value) {
-            dim3 grid(gk.NTg, Np);
+            if (np < 0) np = Np;
+            dim3 grid(gk.NTg, np);
+            GdFusedK k = gk; k.plane0 = p0;
             const Cplx* F = Fg + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
-            cols_entry->gd<<<grid, 576, smem_col, st>>>(gk, tw_col, tw_col_rev, Tg, F);
+            cols_entry->gd<<<grid, 576, smem_col, st>>>(k, tw_col, tw_col_rev, Tg, F);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -877,7 +907,60 @@ struct Plan : lpc_plan_s {
         return rc;
     }
 
+    // plane range of chain c
+    void chain_range(int c, int* p0, int* np) const {
+        const int base = Np / n_chains, extra = Np % n_chains;
+        *p0 = c * base + (c < extra ? c : extra);
+        *np = base + (c < extra ? 1 : 0);
+    }
+    // The planes of a plan are independent problems, so the fused engine runs them as
+    // n_chains concurrent kernel chains: the DRAM-bound spatial kernel of one plane overlaps with the
+    // latency-bound column kernel of another.  Forked from / joined to `st` with events (also under
+    // stream capture, where this becomes a forked CUDA graph).
+    int iterate_chains(int n_iter, cudaStream_t st) {
+        int rc = LPC_OK;
+        LPC_CK(cudaEventRecord(ev_fork, st));
+        for (int c = 1; c < n_chains; ++c) LPC_CK(cudaStreamWaitEvent(side[c], ev_fork, 0));
+        for (int it = 0; it < n_iter; ++it) {
+            T scalar = T(0);
+            int first = 0, upd_mode = LPC_GD_UPD_GD;
+            if (gd2) {
+                if (algo == LPC_ALGO_NESTEROV) { scalar = (T)nmu; upd_mode = LPC_GD_UPD_NESTEROV; }
+                if (algo == LPC_ALGO_FISTA) {
+                    const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;  // gd.py:238
+                    scalar = (T)((tk - 1.0) / tn);
+                    first = fista_first ? 1 : 0;
+                    upd_mode = LPC_GD_UPD_FISTA;
+                    tk = tn;
+                    fista_first = false;
+                }
+            }
+            for (int c = 0; c < n_chains; ++c) {
+                cudaStream_t cs = c == 0 ? st : side[c];
+                int p0, np;
+                chain_range(c, &p0, &np);
+                if (v2) {
+                    if (!vh_valid && (rc = launch_rows_ifft(cs, p0, np))) return rc;
+                    if ((rc = launch_rows_spatial(cs, eta[eta_cur], eta[eta_cur ^ 1], p0, np))) return rc;
+                    if ((rc = launch_cols(cs, p0, np))) return rc;
+                } else {
+                    if ((rc = gd2_cols(0, cs, p0, np))) return rc;
+                    if ((rc = gd2_rows(LPC_GD_RESID, T(0), 0, cs, p0, np))) return rc;
+                    if ((rc = gd2_cols(1, cs, p0, np))) return rc;
+                    if ((rc = gd2_rows(upd_mode, scalar, first, cs, p0, np))) return rc;
+                }
+            }
+            if (v2) { eta_cur ^= 1; vh_valid = false; }
+        }
+        for (int c = 1; c < n_chains; ++c) {
+            LPC_CK(cudaEventRecord(ev_join[c], side[c]));
+            LPC_CK(cudaStreamWaitEvent(st, ev_join[c], 0));
+        }
+        return LPC_OK;
+    }
+
     int iterate(int n_iter, cudaStream_t st) {
+        if ((v2 || gd2) && n_chains > 1) return iterate_chains(n_iter, st);
         int rc = LPC_OK;
         for (int i = 0; i < n_iter && rc == LPC_OK; ++i) rc = (algo == LPC_ALGO_ADMM) ? admm_iteration(st) : gd_iteration(st);
         return rc;
@@ -1091,7 +1174,6 @@ int lpc_plan_create(lpc_plan_t* out, int device, int algo, int dtype, int norm, 
     if (C != 1 && C != 3) return bad(LPC_EINVAL, "PSF must either be rgb (3) or grayscale (1) (recon.py:256)");
     if (B < 1 || D < 1 || h < 1 || w < 1) return bad(LPC_EINVAL, "B, D, h, w must be >= 1");
     if ((int64_t)B * D * C > 65535) return bad(LPC_EINVAL, "B*D*C must be <= 65535 planes per plan");
-    if (flags & LPC_FLAG_LITERAL) return bad(LPC_ENOTIMPL, "LPC_FLAG_LITERAL (6-FFT debug order) is not built yet");
     lpc_plan_s* p = nullptr;
     if (dtype == LPC_F32) p = new (std::nothrow) Plan<float>();
     else p = new (std::nothrow) Plan<double>();

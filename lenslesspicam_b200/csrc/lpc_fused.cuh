@@ -53,7 +53,7 @@ constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIAN
 struct FusedK {
     int Hp, Wp, Nh, NT;  // NT tiles of LPC_NCT columns cover Nh = Wp/2+1
     int n_planes, DC;
-    int rows_per_band, bands_per_plane;
+    int plane0;  // first plane of this launch (the planes of a plan are split over concurrent streams)
 };
 
 constexpr int LPC_ROWS_RY = 4;  // rows a B2 CTA processes back to back
@@ -112,7 +112,7 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* W = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int row = blockIdx.x, p = blockIdx.y;
+    const int row = blockIdx.x, p = f.plane0 + blockIdx.y;
     const int Hp = f.Hp;
     const int64_t tile_stride = (int64_t)Hp * (2 * NCT);
     const C* src0 = Tin + (int64_t)p * NT * tile_stride + (int64_t)row * (2 * NCT);
@@ -181,7 +181,7 @@ k_rows_fft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const T* __re
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* W = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int row = blockIdx.x, p = blockIdx.y;
+    const int row = blockIdx.x, p = f.plane0 + blockIdx.y;
     const int64_t plane = (int64_t)f.Hp * Wp;
     const T* Vin = VH + (int64_t)p * plane + (int64_t)row * Wp;
     const T* HVin = Vin + (int64_t)f.n_planes * plane;
@@ -209,7 +209,7 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* W = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int p = blockIdx.y;
+    const int p = f.plane0 + blockIdx.y;
     const int Hp = f.Hp;
     const int64_t plane = (int64_t)Hp * Wp;
     const int64_t base = (int64_t)p * plane;
@@ -348,7 +348,7 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ twF, const typen
     const int tid = threadIdx.x;
     const int NT = f.NT;
     const int tile = blockIdx.x;
-    const int p = blockIdx.y;
+    const int p = f.plane0 + blockIdx.y;
     const int q = p % f.DC;
     const C* src = Tsrc + ((int64_t)p * NT + tile) * n;
     C* dst = Tdst + ((int64_t)p * NT + tile) * n;

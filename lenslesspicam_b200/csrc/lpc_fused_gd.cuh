@@ -36,6 +36,7 @@ struct GdFusedK {
     int Hp, Wp, Nh, NTg;
     int h, w, sy, sx;
     int n_planes, DC, C, D, Dd;
+    int plane0;  // first plane of this launch
 };
 
 enum { LPC_GD_INIT = 0, LPC_GD_RESID = 1, LPC_GD_UPD_GD = 2, LPC_GD_UPD_NESTEROV = 3, LPC_GD_UPD_FISTA = 4 };
@@ -73,7 +74,7 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* W = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int p = blockIdx.y;
+    const int p = f.plane0 + blockIdx.y;
     const int ra = 2 * blockIdx.x, rb = ra + 1;
     const int h = f.h, w = f.w, sx = f.sx;
     const bool has_b = rb < h;
@@ -221,7 +222,7 @@ k_gd_cols(GdFusedK f, const typename CxT<T>::type* __restrict__ twF, const typen
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* sm = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x, p = blockIdx.y;
+    const int tile = blockIdx.x, p = f.plane0 + blockIdx.y;
     const int q = p % f.DC;
     const int h = f.h, sy = f.sy;
     C* blk = Tg + ((int64_t)p * f.NTg + tile) * (int64_t)h * NC;
