@@ -11,7 +11,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblpc.so")
+# LPC_LIB_PATH: load another build of the same C-ABI (A/B experiments: e.g. -DLPC_PACKED2=0)
+LIB_PATH = os.environ.get("LPC_LIB_PATH") or os.path.join(_HERE, "liblpc.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0

@@ -17,6 +17,7 @@
 #include "lpc_fft_plan.h"
 #include "lpc_fused.cuh"
 #include "lpc_fused_gd.cuh"
+#include "lpc_fused_tma.cuh"
 #include "lpc_gd.cuh"
 #include "lpc_setup.cuh"
 #include "lpc_util.cuh"
@@ -67,7 +68,13 @@ using GdRowsKern = void (*)(GdFusedK, const float2*, const float2*, float2*, con
                             float, int);
 using GdColsKern = void (*)(GdFusedK, const float2*, const float2*, float2*, const float2*);
 struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; GdRowsKern gd[5]; };
-struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; };
+using ColsTmaKern = void (*)(FusedK, ColsTmaK, int, const float2*, const float2*, float2*, const float2*, const float*,
+                             const float2*);
+constexpr int LPC_TMA_NTHG1 = 960, LPC_TMA_NTHG2 = 480;  // threads per compute group: one group / two groups
+constexpr int LPC_TMA_NTHG3 = 288;  // three groups, no look-ahead buffer
+constexpr int LPC_TMA_NV = 5;
+constexpr int LPC_TMA_G[LPC_TMA_NV] = {1, 2, 3, 2, 2}, LPC_TMA_T[LPC_TMA_NV] = {960, 480, 288, 288, 384};
+struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; ColsTmaKern tma[LPC_TMA_NV]; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
 #define LPC_X(N, ...)                                                                                   \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_rows_ifft<float, FftSeq<N, __VA_ARGS__>>,              \
@@ -81,7 +88,10 @@ const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
 #undef LPC_X
 #define LPC_X(N, ...) \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, {k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 1024, 1>, k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>}, \
-     k_gd_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>},
+     k_gd_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>,                                                              \
+     {k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 1, LPC_TMA_NTHG1>, k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, LPC_TMA_NTHG2>,                          \
+      k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 3, LPC_TMA_NTHG3>, k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 288>, \
+      k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 384>}},
 const ColsEntry g_cols_menu[] = {LPC_COL_MENU(LPC_X)};
 #undef LPC_X
 const RowsEntry* find_rows(int N) {
@@ -169,6 +179,15 @@ struct Plan : lpc_plan_s {
     Cplx* tw_row_rev = nullptr;  // tables of the reversed radix sequences (the transform on the other side
     Cplx* tw_col_rev = nullptr;  // of an in-register fused pass runs the reversed order)
     Cplx* spec1 = nullptr;  // [Np][splane], warm start only (lazily allocated)
+    // persistent TMA-pipelined column kernel (lpc_fused_tma.cuh)
+    int cols_tma = 0;        // 0 = off (k_admm_cols), 1 / 2 / 3 = number of compute groups
+    Cplx* tabs_ip = nullptr; // twiddles of the in-place passes | Wj | Sy0 (copied to shared memory by the kernel)
+    Cplx* Hm = nullptr;      // H in middle-stage order [DC][NT][RL][Hp/RL][NCT]
+    T* Gx = nullptr;         // 2 - 2cos(2 pi kx/Wp), [NT*NCT]
+    int* kymap = nullptr;    // position -> frequency after the forward passes
+    ColsTmaK ctk{};          // cos/sin/phase of the innermost digit (mu's and scale are filled per launch)
+    size_t smem_cols_tma = 0;
+    int n_sms = 148;
     FftPlan plan_row{}, plan_col{};
     FusedK fk{};
     size_t smem_row = 0, smem_col = 0;
@@ -340,7 +359,8 @@ struct Plan : lpc_plan_s {
         }
         if ((rc = bind_work())) return rc;
         if (v2 || gd2) {
-            int want = 3;
+            // the persistent column kernel owns whole SMs (3 tile buffers), so it runs all planes in one chain
+            int want = (v2 && cols_tma) ? 1 : 3;
             if (const char* e = getenv("LPC_CHAINS")) want = atoi(e);
             if (want > MAX_CHAINS) want = MAX_CHAINS;
             if (want > Np) want = Np;
@@ -424,6 +444,19 @@ struct Plan : lpc_plan_s {
             if (np < 0) np = Np;
             dim3 grid(fk.NT, np);
             FusedK k = fk; k.plane0 = p0;
+            if (cols_tma) {
+                const int n_items = fk.NT * np;
+                const int nthr = LPC_TMA_G[cols_tma - 1] * LPC_TMA_T[cols_tma - 1] + 32;
+                const int nblk = n_items < n_sms ? n_items : n_sms;
+                if constexpr (std::is_same<T, float>::value) {
+                    ColsTmaK ck = ctk;
+                    ck.mu1 = (float)mu1; ck.mu2 = (float)mu2; ck.mu3 = (float)mu3;
+                    ck.scale = (float)(0.5 / ((double)Hp * (double)Wp));
+                    cols_entry->tma[cols_tma - 1]<<<nblk, nthr, smem_cols_tma, st>>>(k, ck, n_items, tabs_ip, Tout, Tin, Hm, Gx, Sx);
+                }
+                LPC_KCHECK();
+                return LPC_OK;
+            }
             cols_entry->kern[cols_variant]<<<grid, cols_variant ? 576 : 1024, smem_col, st>>>(k, tw_col, tw_col_rev, Tout, Tin, Ht, Rt, Sy, Sx);
             LPC_KCHECK();
         }
@@ -464,10 +497,65 @@ struct Plan : lpc_plan_s {
             if ((rc = alloc(&Ht, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
             if ((rc = alloc(&Rt, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
             if ((rc = upload_twiddles())) return rc;
+            if ((rc = init_cols_tma(max_optin))) return rc;
             v2 = true;
             return LPC_OK;
         }
     }
+    // persistent TMA-pipelined column kernel: tables in the order its in-register middle stage wants
+    int init_cols_tma(int max_optin) {
+        if constexpr (!std::is_same<T, float>::value) {
+            return LPC_OK;
+        } else {
+            // measured at 2160 (A per launch): 1x960 232 us, 2x480 175, 3x288 160, 2x384 155, 2x288 147 (96 registers,
+            // no spills, look-ahead buffer); k_admm_cols (LPC_COLS_TMA=0) 208
+            int want = 4;
+            if (const char* e = getenv("LPC_COLS_TMA")) want = atoi(e);
+            if (want < 0 || want > LPC_TMA_NV) want = 4;
+            const int np = cols_entry->npass, RL = cols_entry->radix[np - 1], NBL = Hp / RL;
+            std::vector<Cplx> tabs;
+            if (!fill_fft_ip_twiddles(Hp, cols_entry->radix, np, &tabs)) return fail(LPC_EINVAL, "fill_fft_ip_twiddles", "menu sequence");
+            int tw_len = 0;
+            for (int i = 0, M = Hp; i < np; ++i) { tw_len += (cols_entry->radix[i] - 1) * (M / cols_entry->radix[i]); M /= cols_entry->radix[i]; }
+            tabs.resize((size_t)tw_len);  // (fill pads an empty table with one entry)
+            smem_cols_tma = cols_tma_smem_bytes(Hp, RL, tw_len);
+            if (want == 0 || RL > LPC_TMA_MAXR || smem_cols_tma > (size_t)max_optin) return LPC_OK;
+            LPC_CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+            for (int v = 0; v < LPC_TMA_NV; ++v)
+                LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->tma[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols_tma));
+            // position -> frequency after the forward passes; ky(j, m) = ky0(j) + m*NBL
+            std::vector<int> km(Hp);
+            for (int pz = 0; pz < Hp; ++pz) km[pz] = fft_ip_freq_of_pos(Hp, cols_entry->radix, np, pz);
+            const int h2 = Hp / 2;
+            auto phase = [&](long long num, int den) {  // exp(2 pi i num/den), exact integer phase reduction
+                const double a = 2.0 * M_PI * (double)(num % den) / (double)den;
+                Cplx c; c.x = (T)std::cos(a); c.y = (T)std::sin(a); return c;
+            };
+            for (int j = 0; j < NBL; ++j) tabs.push_back(phase(km[j * RL], Hp));                    // Wj
+            for (int j = 0; j < NBL; ++j) tabs.push_back(phase((long long)km[j * RL] * h2, Hp));    // Sy0
+            for (int m = 0; m < RL; ++m) {
+                if (km[m] != m * NBL) return fail(LPC_EINVAL, "init_cols_tma", "innermost digit is not the top digit");
+                const Cplx w = phase(m, RL);
+                ctk.cm[m] = w.x; ctk.sm[m] = w.y;
+                const Cplx sy = phase((long long)m * NBL * h2, Hp);
+                ctk.sym[m].x = sy.x; ctk.sym[m].y = sy.y;
+            }
+            int rc;
+            if ((rc = alloc(&tabs_ip, tabs.size()))) return rc;
+            LPC_CK(cudaMemcpy(tabs_ip, tabs.data(), tabs.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            if ((rc = alloc(&kymap, (size_t)Hp))) return rc;
+            LPC_CK(cudaMemcpy(kymap, km.data(), (size_t)Hp * sizeof(int), cudaMemcpyHostToDevice));
+            const int NT = (Nh + LPC_NCT - 1) / LPC_NCT;
+            std::vector<T> gx((size_t)NT * LPC_NCT);
+            for (int kx = 0; kx < NT * LPC_NCT; ++kx) gx[kx] = (T)(2.0 - 2.0 * std::cos(2.0 * M_PI * (double)(kx % Wp) / (double)Wp));
+            if ((rc = alloc(&Gx, gx.size()))) return rc;
+            LPC_CK(cudaMemcpy(Gx, gx.data(), gx.size() * sizeof(T), cudaMemcpyHostToDevice));
+            if ((rc = alloc(&Hm, (size_t)DC * NT * Hp * LPC_NCT))) return rc;
+            cols_tma = want;
+            return LPC_OK;
+        }
+    }
+
     // ---------------------------------------------------------------- GD family on the fused engine
     int init_gd2() {
         if constexpr (!std::is_same<T, float>::value) {
@@ -548,6 +636,12 @@ struct Plan : lpc_plan_s {
     int tile_HR(cudaStream_t st) {
         k_tile_HR<T><<<1184, 256, 0, st>>>(Hc, Rn, Ht, Rt, DC, Hp, Nh, fk.NT);
         LPC_KCHECK();
+        if constexpr (std::is_same<T, float>::value) {
+            if (cols_tma) {
+                k_tile_H_mid<T><<<1184, 256, 0, st>>>(Hc, kymap, Hm, DC, Hp, Nh, fk.NT, cols_entry->radix[cols_entry->npass - 1]);
+                LPC_KCHECK();
+            }
+        }
         return LPC_OK;
     }
     // V, HV of the current iterate -> VH (they are not stored by the fused engine)

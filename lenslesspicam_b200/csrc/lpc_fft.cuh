@@ -31,8 +31,20 @@ template <typename T> struct CxT;
 template <> struct CxT<float> { using type = float2; };
 template <> struct CxT<double> { using type = double2; };
 
+// Blackwell packed fp32x2 arithmetic (FADD2 / FFMA2, sm_100+): one instruction per complex add / subtract
+// instead of two, bit-identical to the scalar form (a - b == fma(b, -1, a) exactly).  MEASURED on B200
+// (profiles/README.md, round 1 session 2): 23 % fewer floating-point instructions, but no faster -- column
+// kernel 174.6 vs 172.4 us, B1 114 vs 111 us, FISTA-300 96.9 vs 93.3 ms -- the FFT kernels are bound by
+// latency and the LSU pipe, not by instruction issue.  Off by default; -DLPC_PACKED2=1 builds it.
+#ifndef LPC_PACKED2
+#define LPC_PACKED2 0
+#endif
 template <typename C> LPC_HD C cx_add(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> LPC_HD C cx_sub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && LPC_PACKED2
+template <> __device__ __forceinline__ float2 cx_add<float2>(float2 a, float2 b) { return __fadd2_rn(a, b); }
+template <> __device__ __forceinline__ float2 cx_sub<float2>(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+#endif
 template <typename C> LPC_HD C cx_mul(C a, C b) { C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
 // multiply by -i (DIR = -1, forward) or +i (DIR = +1, inverse)
 template <int DIR, typename C> LPC_HD C cx_rot(C a) {
@@ -172,6 +184,59 @@ LPC_HD void fft_bfly_store(typename CxT<T>::type* sm, int base, int es, int pads
     for (int m = 0; m < R; ++m) sm[fft_pad(base + (j0 + m * Ns) * es, padsh)] = v[m];
 }
 
+// ----------------------------------------------------------------------------------------
+// In-place decimation passes (no autosort), used where the data meets an element-wise stage
+// between a forward and an inverse transform (the column kernel of lpc_fused_tma.cuh):
+//   forward = decimation in frequency: natural order in, mixed-radix digit-reversed order out;
+//   inverse = its mirror image, decimation in time: digit-reversed in, natural out.
+// A butterfly reads and writes the SAME R addresses, so a pass needs ONE barrier (not the two of
+// a Stockham pass), nothing is staged in registers across the barrier, and any number of threads
+// can walk the butterflies of a pass.  The element-wise stage works in the permuted order (its
+// tables are permuted once per PSF).
+//
+// Pass over blocks of size M (M = N / product of the radices of the earlier DIF passes), radix R,
+// stride S = M/R: butterfly j -> block j / S, offset n2 = j % S, elements blk*M + n2 + m*S.
+//   DIF: v <- DFT_R(v);  v[k1] *= w_M^(n2*k1)          DIT: v[k1] *= w_M^(n2*k1);  v <- DFT_R(v)
+// tw = this pass's table [(k1-1)*S + n2] = exp(-2*pi*i*n2*k1/M) (conjugated for DIR > 0); a pass
+// with S == 1 has no twiddles.  After all DIF passes position p holds frequency fft_ip_freq_of_pos(p).
+// ----------------------------------------------------------------------------------------
+template <typename T, int R, int DIR, bool DIF>
+LPC_HD void fft_ip_bfly(typename CxT<T>::type* sm, int es, int M, int j, const typename CxT<T>::type* tw) {
+    using C = typename CxT<T>::type;
+    const int S = M / R;
+    const int blk = j / S, n2 = j - blk * S;
+    C* p = sm + (blk * M + n2) * es;
+    C v[R];
+#pragma unroll
+    for (int m = 0; m < R; ++m) v[m] = p[m * S * es];
+    if (DIF) Dft<T, R, DIR>::run(v);
+    if (S > 1) {
+#pragma unroll
+        for (int m = 1; m < R; ++m) {
+            C w = tw[(m - 1) * S + n2];  // plain load: the table may live in shared memory
+            if (DIR > 0) w.y = -w.y;
+            v[m] = cx_mul(v[m], w);
+        }
+    }
+    if (!DIF) Dft<T, R, DIR>::run(v);
+#pragma unroll
+    for (int m = 0; m < R; ++m) p[m * S * es] = v[m];
+}
+
+// frequency index held at position p after the forward (DIF) passes with radices r[0..npass)
+LPC_HD int fft_ip_freq_of_pos(int N, const int* r, int npass, int p) {
+    int k = 0, mult = 1, M = N;
+    for (int i = 0; i < npass; ++i) {
+        const int S = M / r[i];
+        const int a = p / S;
+        p -= a * S;
+        k += a * mult;
+        mult *= r[i];
+        M = S;
+    }
+    return k;
+}
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------
 // CTA-cooperative in-place FFT with a COMPILE-TIME radix sequence.
@@ -283,6 +348,69 @@ template <typename T, typename SEQ, int DIR, int NB, int NTH> struct CtaFftStati
 template <typename T, int N, int... Rs, int DIR, int NB, int NTH> struct CtaFftStatic<T, FftSeq<N, Rs...>, DIR, NB, NTH> {
     static __device__ __forceinline__ void run(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid) {
         cta_fft_static_passes<T, DIR, NB, NTH, FftSeq<N, Rs...>::padsh, N, 1, 0, Rs...>(sm, tw, tid);
+    }
+};
+// ---- barrier policies: the whole CTA, or a named barrier shared by a group of COUNT threads
+struct BarCta {
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+template <int COUNT> struct BarNamed {
+    int id;  // 1..15 (0 is __syncthreads)
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory"); }
+};
+
+// ---- one in-place pass walked by NTH threads over NB interleaved transforms of length N
+template <typename T, int R, int DIR, bool DIF, int NB, int NTH, int N, int M>
+__device__ __forceinline__ void cta_fft_ip_pass(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid) {
+    constexpr int total = (N / R) * NB;
+#pragma unroll 1
+    for (int g = tid; g < total; g += NTH) {
+        const int b = g % NB, j = g / NB;
+        fft_ip_bfly<T, R, DIR, DIF>(sm + b, NB, M, j, tw);
+    }
+}
+// forward: all DIF passes but the last (radix R_last, S = 1, no twiddles -- the caller fuses it with its
+// element-wise stage); a barrier separates consecutive passes, NONE follows the last one: the caller issues
+// whatever it wants in flight across that barrier (prefetches), then syncs itself
+template <typename T, int DIR, int NB, int NTH, int N, int M, int TWOFF, bool FIRST, typename BAR, int R, int... Rest>
+__device__ __forceinline__ void cta_fft_ip_dif_butlast(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
+    if constexpr (sizeof...(Rest) > 0) {
+        if constexpr (!FIRST) bar.sync();
+        cta_fft_ip_pass<T, R, DIR, true, NB, NTH, N, M>(sm, tw + TWOFF, tid);
+        cta_fft_ip_dif_butlast<T, DIR, NB, NTH, N, M / R, TWOFF + (R - 1) * (M / R), false, BAR, Rest...>(sm, tw, tid, bar);
+    }
+}
+// inverse: all DIT passes but the innermost (the caller has done it), innermost first; a barrier
+// PRECEDES every pass (so the first one also orders the caller's stage before the first pass)
+template <typename T, int DIR, int NB, int NTH, int N, int M, int TWOFF, typename BAR, int R, int... Rest>
+__device__ __forceinline__ void cta_fft_ip_dit_butinner(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
+    if constexpr (sizeof...(Rest) > 0) {
+        cta_fft_ip_dit_butinner<T, DIR, NB, NTH, N, M / R, TWOFF + (R - 1) * (M / R), BAR, Rest...>(sm, tw, tid, bar);
+        bar.sync();
+        cta_fft_ip_pass<T, R, DIR, false, NB, NTH, N, M>(sm, tw + TWOFF, tid);
+    }
+}
+
+template <typename SEQ> struct IpTraits;
+template <int N_, int... Rs> struct IpTraits<FftSeq<N_, Rs...>> {
+    using Seq = FftSeq<N_, Rs...>;
+    static constexpr int N = N_;
+    static constexpr int npass = sizeof...(Rs);
+    static constexpr int last = Seq::radix[npass - 1];
+    static constexpr int nb_last = N_ / last;  // butterflies of the innermost pass (blocks of `last` consecutive elements)
+    static constexpr int compute_tw_len() {    // entries of the in-place twiddle tables (fill_fft_ip_twiddles)
+        int len = 0, M = N_;
+        for (int i = 0; i < npass; ++i) { len += (Seq::radix[i] - 1) * (M / Seq::radix[i]); M /= Seq::radix[i]; }
+        return len;
+    }
+    static constexpr int tw_len = compute_tw_len();
+    template <typename T, int DIR, int NB, int NTH, typename BAR>
+    static __device__ __forceinline__ void dif_butlast(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
+        cta_fft_ip_dif_butlast<T, DIR, NB, NTH, N_, N_, 0, true, BAR, Rs...>(sm, tw, tid, bar);
+    }
+    template <typename T, int DIR, int NB, int NTH, typename BAR>
+    static __device__ __forceinline__ void dit_butinner(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
+        cta_fft_ip_dit_butinner<T, DIR, NB, NTH, N_, N_, 0, BAR, Rs...>(sm, tw, tid, bar);
     }
 };
 #endif  // __CUDACC__

@@ -94,4 +94,31 @@ inline void fill_fft_twiddles(const FftPlan& plan, std::vector<C>* out) {
     }
 }
 
+// twiddle tables of the in-place decimation passes (fft_ip_bfly): pass i over blocks of size
+// M_i = N / (r[0]*...*r[i-1]) with stride S_i = M_i / r[i] owns (r[i]-1)*S_i entries at offset
+// sum_{i'<i} (r[i']-1)*S_i', entry [(k1-1)*S + n2] = exp(-2*pi*i*n2*k1/M); computed in double
+template <typename C>
+inline bool fill_fft_ip_twiddles(int N, const int* r, int npass, std::vector<C>* out) {
+    long long prod = 1;
+    for (int i = 0; i < npass; ++i) prod *= r[i];
+    if (prod != N) return false;
+    out->clear();
+    int M = N;
+    for (int i = 0; i < npass; ++i) {
+        const int R = r[i], S = M / R;
+        for (int k1 = 1; k1 < R; ++k1)
+            for (int n2 = 0; n2 < S; ++n2) {
+                const long long num = ((long long)n2 * k1) % M;
+                const double ang = -2.0 * M_PI * (double)num / (double)M;
+                C w;
+                w.x = (decltype(w.x))std::cos(ang);
+                w.y = (decltype(w.y))std::sin(ang);
+                out->push_back(w);
+            }
+        M = S;
+    }
+    if (out->empty()) out->push_back(C{});
+    return true;
+}
+
 }  // namespace lpc

@@ -19,7 +19,8 @@
 //
 // "T-layout" of Tin / Tout (tiled-transposed half spectrum), chosen so that BOTH kernels see
 // whole 32-byte sectors:  complex index
-//     ((p*NT + kx/NCT)*Hp + ky)*(2*NCT) + slot*NCT + kx%NCT,     NT = ceil(Nh/NCT), NCT = 2
+//     ((p*NT + kx/NCT)*Hp + ky)*(2*NCT) + (kx%NCT)*2 + slot,     NT = ceil(Nh/NCT), NCT = 2
+// (the two slots of a column are adjacent: the column kernel reads / writes the coupled pair as 16 bytes)
 // A reads/writes one tile (all ky of NCT columns, both slots) as ONE contiguous 2*NCT*Hp*8-byte
 // block; B touches a 2*NCT*8 = 32-byte chunk per (tile, row).
 //
@@ -84,13 +85,13 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
         }
         C* dst = Tdst + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
         if constexpr (sizeof(T) == 4 && NCT == 2) {
-            Vec32f o;  // one 32-byte store per chunk: (A[kx], A[kx+1], Xi[kx], Xi[kx+1])
-            o.v[0] = a[0].x; o.v[1] = a[0].y; o.v[2] = a[1].x; o.v[3] = a[1].y;
-            o.v[4] = x[0].x; o.v[5] = x[0].y; o.v[6] = x[1].x; o.v[7] = x[1].y;
+            Vec32f o;  // one 32-byte store per chunk: (A[kx], Xi[kx], A[kx+1], Xi[kx+1])
+            o.v[0] = a[0].x; o.v[1] = a[0].y; o.v[2] = x[0].x; o.v[3] = x[0].y;
+            o.v[4] = a[1].x; o.v[5] = a[1].y; o.v[6] = x[1].x; o.v[7] = x[1].y;
             st32(reinterpret_cast<float*>(dst), o);
         } else {
 #pragma unroll
-            for (int c = 0; c < NCT; ++c) { dst[c] = a[c]; dst[NCT + c] = x[c]; }
+            for (int c = 0; c < NCT; ++c) { dst[2 * c] = a[c]; dst[2 * c + 1] = x[c]; }
         }
     }
     __syncthreads();
@@ -129,13 +130,13 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     for (int it = 0; it < IT; ++it) {
         const int t = tid + it * NTH;
         if (t < NT) {
-            // chunk = (Vhat[kx], Vhat[kx+1], HVhat[kx], HVhat[kx+1])
+            // chunk = (Vhat[kx], HVhat[kx], Vhat[kx+1], HVhat[kx+1])
 #pragma unroll
             for (int c = 0; c < NCT; ++c) {
                 const int kx = t * NCT + c;
                 C vh, hh;
-                vh.x = ch[it].v[2 * c]; vh.y = ch[it].v[2 * c + 1];
-                hh.x = ch[it].v[4 + 2 * c]; hh.y = ch[it].v[4 + 2 * c + 1];
+                vh.x = ch[it].v[4 * c]; vh.y = ch[it].v[4 * c + 1];
+                hh.x = ch[it].v[4 * c + 2]; hh.y = ch[it].v[4 * c + 3];
                 if (kx < Nh) {
                     C y; y.x = vh.x - hh.y; y.y = vh.y + hh.x;
                     W[fft_pad(kx, PADSH)] = y;
@@ -319,7 +320,7 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// A: one CTA owns one tile: LPC_NCT columns x 2 slots = 4 interleaved column transforms of
+// A: one CTA owns one tile: LPC_NCT columns x 2 slots = 4 interleaved column transforms (index 2*column + slot) of
 // length Hp, resident in shared memory from the load to the store.
 //     forward column FFT of (2A_row, 2Xi_row)      radix sequence SEQ
 //     Vhat  = Rn * (A - S*conj(H)*Xi)        HVhat = S*H*Vhat        (Rn carries 1/(2*Hp*Wp))
@@ -392,8 +393,8 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ twF, const typen
         const int g = tid + it * NTH;
         if (MAXP * NTH == totalp || g < totalp) {
             const int c = g % NCT, j = g / NCT;
-            fft_bfly_load<T, RL>(sm, c, NB, PF, Hp, j, v0[it]);
-            fft_bfly_load<T, RL>(sm, NCT + c, NB, PF, Hp, j, v1[it]);
+            fft_bfly_load<T, RL>(sm, 2 * c, NB, PF, Hp, j, v0[it]);
+            fft_bfly_load<T, RL>(sm, 2 * c + 1, NB, PF, Hp, j, v1[it]);
             fft_bfly_compute<T, RL, -1>(v0[it], twF + TR::tw_off_last, NSL, j);
             fft_bfly_compute<T, RL, -1>(v1[it], twF + TR::tw_off_last, NSL, j);
             const int kx = tile * NCT + c;
@@ -423,8 +424,8 @@ k_admm_cols(FusedK f, const typename CxT<T>::type* __restrict__ twF, const typen
         const int g = tid + it * NTH;
         if (MAXP * NTH == totalp || g < totalp) {
             const int c = g % NCT, j = g / NCT;
-            fft_bfly_store<T, RL>(sm, c, NB, PI, 1, j, v0[it]);
-            fft_bfly_store<T, RL>(sm, NCT + c, NB, PI, 1, j, v1[it]);
+            fft_bfly_store<T, RL>(sm, 2 * c, NB, PI, 1, j, v0[it]);
+            fft_bfly_store<T, RL>(sm, 2 * c + 1, NB, PI, 1, j, v1[it]);
         }
     }
     __syncthreads();

@@ -105,6 +105,68 @@ template <typename T, int DIR> static double test_fft(int N, int nbatch, bool in
     return err / mx;
 }
 
+
+// ---- in-place decimation passes (fft_ip_bfly): forward DIF -> permuted spectrum -> inverse DIT
+template <typename T, int R, int DIR, bool DIF>
+static void emu_ip_pass(std::vector<typename CxT<T>::type>& sm, const typename CxT<T>::type* tw, int N, int M, int nbatch) {
+    const int total = (N / R) * nbatch;
+    for (int g = 0; g < total; ++g) {  // butterflies touch disjoint addresses: any order is valid
+        const int b = g % nbatch, j = g / nbatch;
+        fft_ip_bfly<T, R, DIR, DIF>(sm.data() + b, nbatch, M, j, tw);
+    }
+}
+template <typename T, int DIR, bool DIF>
+static void emu_ip_dispatch(int R, std::vector<typename CxT<T>::type>& sm, const typename CxT<T>::type* tw, int N, int M, int nbatch) {
+    switch (R) {
+#define CASE(RR) case RR: emu_ip_pass<T, RR, DIR, DIF>(sm, tw, N, M, nbatch); break;
+        CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(9) CASE(10) CASE(12) CASE(15) CASE(16)
+#undef CASE
+        default: printf("bad radix %d\n", R); exit(2);
+    }
+}
+template <typename T> static double test_ip(int N, int nbatch) {
+    using C = typename CxT<T>::type;
+    FftPlan plan;
+    if (!make_fft_plan(N, &plan)) { printf("no plan for %d\n", N); exit(2); }
+    std::vector<C> tw;
+    if (!fill_fft_ip_twiddles(N, plan.radix, plan.npass, &tw)) { printf("no ip twiddles for %d\n", N); exit(2); }
+    std::vector<C> sm((size_t)N * nbatch);
+    std::vector<std::vector<std::complex<long double>>> x(nbatch, std::vector<std::complex<long double>>(N));
+    for (int b = 0; b < nbatch; ++b)
+        for (int i = 0; i < N; ++i) {
+            C c; c.x = (T)(rand() / (double)RAND_MAX - 0.5); c.y = (T)(rand() / (double)RAND_MAX - 0.5);
+            sm[(size_t)i * nbatch + b] = c;
+            x[b][i] = {c.x, c.y};
+        }
+    std::vector<int> off(plan.npass), Ms(plan.npass);
+    int M = N, o = 0;
+    for (int i = 0; i < plan.npass; ++i) { Ms[i] = M; off[i] = o; o += (plan.radix[i] - 1) * (M / plan.radix[i]); M /= plan.radix[i]; }
+    for (int i = 0; i < plan.npass; ++i) emu_ip_dispatch<T, -1, true>(plan.radix[i], sm, tw.data() + off[i], N, Ms[i], nbatch);
+    double err = 0, mx = 0;
+    for (int b = 0; b < nbatch; ++b) {
+        std::vector<std::complex<long double>> X;
+        naive<T, -1>(x[b], X);
+        for (int p = 0; p < N; ++p) {
+            const int k = fft_ip_freq_of_pos(N, plan.radix, plan.npass, p);
+            C c = sm[(size_t)p * nbatch + b];
+            err = fmax(err, (double)std::abs(std::complex<long double>(c.x, c.y) - X[k]));
+            mx = fmax(mx, (double)std::abs(X[k]));
+        }
+    }
+    // mirror image back: innermost pass first
+    for (int i = plan.npass - 1; i >= 0; --i) emu_ip_dispatch<T, +1, false>(plan.radix[i], sm, tw.data() + off[i], N, Ms[i], nbatch);
+    double err2 = 0;
+    for (int b = 0; b < nbatch; ++b)
+        for (int i = 0; i < N; ++i) {
+            C c = sm[(size_t)i * nbatch + b];
+            err2 = fmax(err2, (double)std::abs(std::complex<long double>(c.x / N, c.y / N) - x[b][i]));
+        }
+    printf("N=%5d batch=%d in-place DIF/DIT radices:", N, nbatch);
+    for (int p = 0; p < plan.npass; ++p) printf(" %d", plan.radix[p]);
+    printf("  fwd rel err %.2e  round-trip err %.2e\n", err / mx, err2);
+    return fmax(err / mx, err2);
+}
+
 int main() {
     int bad = 0;
     double e;
@@ -120,6 +182,10 @@ int main() {
         if (test_fft<double, +1>(N, 2, false) > 1e-13) bad++;
         if (test_fft<float, -1>(N, 4, true) > 2e-6) bad++;
         if (test_fft<float, +1>(N, 3, true) > 2e-6) bad++;
+    }
+    for (int N : sizes) {
+        if (test_ip<double>(N, 1) > 1e-13) bad++;
+        if (test_ip<float>(N, 4) > 2e-6) bad++;
     }
     printf(bad ? "FAILED (%d)\n" : "ALL OK\n", bad);
     return bad ? 1 : 0;
