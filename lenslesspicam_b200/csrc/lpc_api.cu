@@ -74,7 +74,8 @@ constexpr int LPC_TMA_NTHG1 = 960, LPC_TMA_NTHG2 = 480;  // threads per compute 
 constexpr int LPC_TMA_NTHG3 = 288;  // three groups, no look-ahead buffer
 constexpr int LPC_TMA_NV = 5;
 constexpr int LPC_TMA_G[LPC_TMA_NV] = {1, 2, 3, 2, 2}, LPC_TMA_T[LPC_TMA_NV] = {960, 480, 288, 288, 384};
-struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; ColsTmaKern tma[LPC_TMA_NV]; };
+using GdColsTmaKern = void (*)(GdFusedK, int, const float2*, float2*, const float2*);
+struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; ColsTmaKern tma[LPC_TMA_NV]; GdColsTmaKern gd_tma; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
 #define LPC_X(N, ...)                                                                                   \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_rows_ifft<float, FftSeq<N, __VA_ARGS__>>,              \
@@ -91,7 +92,8 @@ const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
      k_gd_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>,                                                              \
      {k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 1, LPC_TMA_NTHG1>, k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, LPC_TMA_NTHG2>,                          \
       k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 3, LPC_TMA_NTHG3>, k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 288>, \
-      k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 384>}},
+      k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 384>},                                                       \
+     k_gd_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 288>},
 const ColsEntry g_cols_menu[] = {LPC_COL_MENU(LPC_X)};
 #undef LPC_X
 const RowsEntry* find_rows(int N) {
@@ -198,6 +200,9 @@ struct Plan : lpc_plan_s {
     Cplx* Fg = nullptr;     // [2][DC][NTg][Hp][4]: S*H/(2N) and S*conj(H)/(2N)
     T* xu = nullptr;        // [Np][h][w] image estimate, unpadded planar
     GdFusedK gk{};
+    int gd_tma = 0;          // GD columns on the persistent TMA pipeline (k_gd_cols_tma)
+    Cplx* Fgm = nullptr;     // filters in middle-stage order [2][DC][NTg][RL][Hp/RL][4]
+    size_t smem_gd_tma = 0;
     // independent planes run as concurrent chains on side streams (forked / joined inside lpc_run)
     static constexpr int MAX_CHAINS = 4;
     int n_chains = 1;
@@ -360,12 +365,14 @@ struct Plan : lpc_plan_s {
         if ((rc = bind_work())) return rc;
         if (v2 || gd2) {
             // the persistent column kernel owns whole SMs (3 tile buffers), so it runs all planes in one chain
-            int want = (v2 && cols_tma) ? 1 : 3;
+            int want = ((v2 && cols_tma) || (gd2 && gd_tma)) ? 1 : 3;
             if (const char* e = getenv("LPC_CHAINS")) want = atoi(e);
             if (want > MAX_CHAINS) want = MAX_CHAINS;
             if (want > Np) want = Np;
             if (want < 1) want = 1;
             n_chains = want;
+            if (const char* e = getenv("LPC_PLANE_MAJOR")) plane_major = atoi(e) ? 1 : 0;
+            if (const char* e = getenv("LPC_VH_SHARED")) vh_shared = atoi(e) ? 1 : 0;
             LPC_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
             for (int i = 1; i < n_chains; ++i) {
                 LPC_CK(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
@@ -409,12 +416,12 @@ struct Plan : lpc_plan_s {
     int ry_log2 = 0;       // B2 processes 1 << ry_log2 rows per CTA (measured: 1 row 315 us, 2 rows 400, 4 rows 465)
     int cols_variant = 1;  // A: 0 = 1024 threads x 1 CTA/SM, 1 = 576 threads x 2 CTAs/SM
 
-    int launch_rows_ifft(cudaStream_t st, int p0 = 0, int np = -1) {
+    int launch_rows_ifft(cudaStream_t st, int p0 = 0, int np = -1, T* vh = nullptr) {
         if constexpr (std::is_same<T, float>::value) {
             if (np < 0) np = Np;
             dim3 grid(Hp, np);
             FusedK k = fk; k.plane0 = p0;
-            rows_entry->ifft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, Tin, VH);
+            rows_entry->ifft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, Tin, vh ? vh : VH);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -427,13 +434,13 @@ struct Plan : lpc_plan_s {
         }
         return LPC_OK;
     }
-    int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o, int p0 = 0, int np = -1) {
+    int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o, int p0 = 0, int np = -1, const T* vh = nullptr) {
         if constexpr (std::is_same<T, float>::value) {
             if (np < 0) np = Np;
             const int ry = 1 << ry_log2;
             dim3 grid((Hp + ry - 1) / ry, np);
             FusedK k = fk; k.plane0 = p0;
-            rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, admm_k(), tw_row, VH, Tout, data,
+            rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, admm_k(), tw_row, vh ? vh : VH, Tout, data,
                                                                           AX + (int64_t)Np * plane, rho, eta_i, eta_o);
             LPC_KCHECK();
         }
@@ -556,6 +563,33 @@ struct Plan : lpc_plan_s {
         }
     }
 
+    int init_gd_tma(int max_optin) {
+        if constexpr (!std::is_same<T, float>::value) {
+            return LPC_OK;
+        } else {
+            int want = 1;
+            if (const char* e = getenv("LPC_GD_TMA")) want = atoi(e) ? 1 : 0;
+            const int np = cols_entry->npass, RL = cols_entry->radix[np - 1];
+            std::vector<Cplx> tabs;
+            if (!fill_fft_ip_twiddles(Hp, cols_entry->radix, np, &tabs)) return fail(LPC_EINVAL, "fill_fft_ip_twiddles", "menu sequence");
+            smem_gd_tma = (size_t)LPC_TMA_NBUF * Hp * LPC_GNC * sizeof(Cplx) + 64 + tabs.size() * sizeof(Cplx);
+            // bulk copies need 16-byte aligned addresses: the window starts sy rows (32 bytes each) into the buffer
+            if (!want || RL > LPC_TMA_MAXR || smem_gd_tma > (size_t)max_optin) return LPC_OK;
+            LPC_CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+            LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->gd_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gd_tma));
+            std::vector<int> km(Hp);
+            for (int pz = 0; pz < Hp; ++pz) km[pz] = fft_ip_freq_of_pos(Hp, cols_entry->radix, np, pz);
+            int rc;
+            if ((rc = alloc(&tabs_ip, tabs.size()))) return rc;
+            LPC_CK(cudaMemcpy(tabs_ip, tabs.data(), tabs.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
+            if ((rc = alloc(&kymap, (size_t)Hp))) return rc;
+            LPC_CK(cudaMemcpy(kymap, km.data(), (size_t)Hp * sizeof(int), cudaMemcpyHostToDevice));
+            if ((rc = alloc(&Fgm, (size_t)2 * DC * gk.NTg * Hp * LPC_GNC))) return rc;
+            gd_tma = 1;
+            return LPC_OK;
+        }
+    }
+
     // ---------------------------------------------------------------- GD family on the fused engine
     int init_gd2() {
         if constexpr (!std::is_same<T, float>::value) {
@@ -581,6 +615,7 @@ struct Plan : lpc_plan_s {
             if ((rc = alloc(&Tg, (size_t)Np * gk.NTg * h * LPC_GNC))) return rc;
             if ((rc = alloc(&Fg, (size_t)2 * DC * gk.NTg * Hp * LPC_GNC))) return rc;
             if ((rc = upload_twiddles())) return rc;
+            if ((rc = init_gd_tma(max_optin))) return rc;
             gd2 = true;
             return LPC_OK;
         }
@@ -601,6 +636,13 @@ struct Plan : lpc_plan_s {
             if (np < 0) np = Np;
             dim3 grid(gk.NTg, np);
             GdFusedK k = gk; k.plane0 = p0;
+            if (gd_tma) {
+                const Cplx* Fm_ = Fgm + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
+                const int n_items = gk.NTg * np;
+                cols_entry->gd_tma<<<n_items < n_sms ? n_items : n_sms, 2 * 288 + 32, smem_gd_tma, st>>>(k, n_items, tabs_ip, Tg, Fm_);
+                LPC_KCHECK();
+                return LPC_OK;
+            }
             const Cplx* F = Fg + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
             cols_entry->gd<<<grid, 576, smem_col, st>>>(k, tw_col, tw_col_rev, Tg, F);
             LPC_KCHECK();
@@ -742,6 +784,13 @@ struct Plan : lpc_plan_s {
         if (gd2) {
             k_gd_tile_filter<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, Fg, DC, Hp, Wp, Nh, gk.NTg);
             LPC_KCHECK();
+            if constexpr (std::is_same<T, float>::value) {
+                if (gd_tma) {
+                    k_gd_tile_filter_mid<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, kymap, Fgm, DC, Hp, Wp, Nh, gk.NTg,
+                                                                 cols_entry->radix[cols_entry->npass - 1]);
+                    LPC_KCHECK();
+                }
+            }
         }
         psf_set = true;
         state_ready = false;
@@ -1053,7 +1102,30 @@ struct Plan : lpc_plan_s {
         return LPC_OK;
     }
 
+    // Plane-major order (fused ADMM engine): the planes of a plan are independent problems, so plane p runs ALL its
+    // iterations before plane p+1 starts.  Every producer -> consumer hand-off (A -> B1 through Tin, B1 -> B2 through
+    // V/HV, B2 -> A through Tout) is then 66 MB written and immediately read back, inside the 126 MB L2, instead of
+    // 3 x 66 MB with the other planes' traffic in between; V/HV of every plane share ONE scratch plane pair.
+    int plane_major = 1, vh_shared = 1;
+    int iterate_plane_major(int n_iter, cudaStream_t st) {
+        int rc = LPC_OK;
+        const int eta0 = eta_cur;
+        for (int p = 0; p < Np; ++p) {
+            T* vh = vh_shared ? VH - (int64_t)p * plane : VH;  // plane p of this view is plane 0 of VH (V) / of its HV half
+            for (int it = 0; it < n_iter; ++it) {
+                const int ei = (eta0 + it) & 1;
+                if ((rc = launch_rows_ifft(st, p, 1, vh))) return rc;
+                if ((rc = launch_rows_spatial(st, eta[ei], eta[ei ^ 1], p, 1, vh))) return rc;
+                if ((rc = launch_cols(st, p, 1))) return rc;
+            }
+        }
+        eta_cur = (eta0 + n_iter) & 1;
+        vh_valid = false;
+        return LPC_OK;
+    }
+
     int iterate(int n_iter, cudaStream_t st) {
+        if (v2 && plane_major && n_chains == 1) return iterate_plane_major(n_iter, st);
         if ((v2 || gd2) && n_chains > 1) return iterate_chains(n_iter, st);
         int rc = LPC_OK;
         for (int i = 0; i < n_iter && rc == LPC_OK; ++i) rc = (algo == LPC_ALGO_ADMM) ? admm_iteration(st) : gd_iteration(st);

@@ -27,6 +27,7 @@
 // Reference semantics: admm.py:280-294,320 merged as in DESIGN.md section 3 (identical to k_admm_cols).
 #pragma once
 #include "lpc_fused.cuh"
+#include "lpc_fused_gd.cuh"
 
 namespace lpc {
 
@@ -271,6 +272,168 @@ __global__ void k_tile_H_mid(const typename CxT<T>::type* __restrict__ H, const 
         C h; h.x = h.y = T(0);
         if (kx < Nh) h = H[((int64_t)q * Hp + ky) * Nh + kx];
         Hm[i] = h;
+    }
+}
+
+}  // namespace lpc
+
+// =============================================================================================
+// GD / Nesterov / FISTA: the column kernel of lpc_fused_gd.cuh (column FFT -> filter -> column IFFT on a
+// G-layout tile of LPC_GNC columns) on the same persistent TMA pipeline.  Only the h window rows of a tile
+// exist in HBM (a contiguous h*32-byte block): the producer bulk-copies them to rows sy..sy+h-1 of a tile
+// buffer, the compute group zero-fills the other Hp-h rows (the zero padding, rfft_convolve.py:84-100),
+// transforms in place, multiplies by the filter in registers between the innermost passes, and the
+// producer bulk-stores the window rows back.  Fm: filter in middle-stage order [DC][NTg][RL][Hp/RL][4].
+// =============================================================================================
+namespace lpc {
+
+template <typename T, typename SEQ, int NG, int NTHG>
+__global__ void __launch_bounds__(NG * NTHG + 32, 1)
+k_gd_cols_tma(GdFusedK f, int n_items, const typename CxT<T>::type* __restrict__ tabs, typename CxT<T>::type* Tg,
+              const typename CxT<T>::type* __restrict__ Fm) {
+    using C = typename CxT<T>::type;
+    using IP = IpTraits<SEQ>;
+    static_assert(sizeof(T) == 4 && LPC_GNC == 4, "float only, 32-byte chunks");
+    constexpr int NC = LPC_GNC, NBUF = LPC_TMA_NBUF;
+    constexpr int Hp = SEQ::N, RL = IP::last, NBL = IP::nb_last;
+    constexpr int n = Hp * NC;
+    constexpr uint32_t TILE_BYTES = (uint32_t)n * sizeof(C);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    C* bufs = reinterpret_cast<C*>(smem_raw);
+    const uint32_t bars = smem_u32(smem_raw + (size_t)NBUF * TILE_BYTES);
+    C* tw_s = reinterpret_cast<C*>(smem_raw + (size_t)NBUF * TILE_BYTES + 64);
+    auto full_bar = [&](int b) { return bars + 8u * (uint32_t)b; };
+    auto done_bar = [&](int b) { return bars + 8u * (uint32_t)(NBUF + b); };
+
+    const int tid = threadIdx.x;
+    const int NTg = f.NTg, h = f.h, sy = f.sy;
+    const uint32_t win_bytes = (uint32_t)h * NC * (uint32_t)sizeof(C);
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) { mbar_init(full_bar(b), 1); mbar_init(done_bar(b), NTHG); }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < IP::tw_len; i += NG * NTHG + 32) tw_s[i] = __ldg(tabs + i);
+    __syncthreads();
+    const int count = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid >= NG * NTHG) {
+        if (tid != NG * NTHG) return;
+        auto issue_load = [&](int e) {
+            const int item = (int)blockIdx.x + e * (int)gridDim.x;
+            const int p = f.plane0 + item / NTg, tile = item % NTg, q = p % f.DC;
+            const int b = e % NBUF;
+            mbar_arrive_expect_tx(full_bar(b), win_bytes);
+            bulk_g2s(smem_u32(bufs + (size_t)b * n + (size_t)sy * NC), Tg + ((int64_t)p * NTg + tile) * (int64_t)h * NC, win_bytes,
+                     full_bar(b));
+            bulk_prefetch_l2(Fm + ((int64_t)q * NTg + tile) * (int64_t)n, TILE_BYTES);
+        };
+        for (int e = 0; e < NBUF && e < count; ++e) issue_load(e);
+        for (int e = 0; e < count; ++e) {
+            const int b = e % NBUF;
+            mbar_wait(done_bar(b), (uint32_t)((e / NBUF) & 1));
+            const int item = (int)blockIdx.x + e * (int)gridDim.x;
+            const int p = f.plane0 + item / NTg, tile = item % NTg;
+            bulk_s2g(Tg + ((int64_t)p * NTg + tile) * (int64_t)h * NC, smem_u32(bufs + (size_t)b * n + (size_t)sy * NC), win_bytes);
+            bulk_commit();
+            if (e + NBUF < count) {
+                bulk_wait_read0();
+                issue_load(e + NBUF);
+            }
+        }
+        bulk_wait0();
+        return;
+    }
+
+    const int grp = tid / NTHG, gtid = tid - grp * NTHG;
+    const BarNamed<NTHG> bar{1 + grp};
+    constexpr int NPAIR = NBL * NC;  // (butterfly, column) pairs of the middle stage
+    const int top16 = sy * (NC / 2);                  // 16-byte vectors above the window
+    const int bot0 = (sy + h) * (NC / 2);             // first 16-byte vector below it
+    for (int e = grp; e < count; e += NG) {
+        const int b = e % NBUF;
+        C* sm = bufs + (size_t)b * n;
+        const int item = (int)blockIdx.x + e * (int)gridDim.x;
+        const int p = f.plane0 + item / NTg, tile = item % NTg, q = p % f.DC;
+        const C* Fq = Fm + ((int64_t)q * NTg + tile) * (int64_t)n;
+        mbar_wait(full_bar(b), (uint32_t)((e / NBUF) & 1));
+        // zero padding around the window: the bulk copy only writes the window rows, the others hold the output of
+        // the buffer's previous tile.  Only now is the buffer ours -- its previous tile may belong to the OTHER
+        // group, and the load completing is what proves that tile was computed and stored.
+        {
+            float4* z = reinterpret_cast<float4*>(sm);
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = gtid; i < top16; i += NTHG) z[i] = zero;
+            for (int i = bot0 + gtid; i < n / 2; i += NTHG) z[i] = zero;
+        }
+        bar.sync();  // the zero rows of every thread are in place
+        IP::template dif_butlast<T, -1, NC, NTHG>(sm, tw_s, gtid, bar);
+        int g = gtid;
+        C Fv[RL];
+        if (g < NPAIR) {
+            const int c = g % NC, j = g / NC;
+#pragma unroll
+            for (int m = 0; m < RL; ++m) Fv[m] = __ldg(Fq + (m * NBL + j) * NC + c);
+        }
+        bar.sync();
+#pragma unroll 1
+        while (g < NPAIR) {
+            const int c = g % NC, j = g / NC;
+            C* pp = sm + (size_t)(j * RL) * NC + c;
+            C v[RL];
+#pragma unroll
+            for (int m = 0; m < RL; ++m) v[m] = pp[m * NC];
+            Dft<T, RL, -1>::run(v);
+#pragma unroll
+            for (int m = 0; m < RL; ++m) v[m] = cx_mul(v[m], Fv[m]);
+            const int gn = g + NTHG;
+            if (gn < NPAIR) {
+                const int cn = gn % NC, jn = gn / NC;
+#pragma unroll
+                for (int m = 0; m < RL; ++m) Fv[m] = __ldg(Fq + (m * NBL + jn) * NC + cn);
+            }
+            Dft<T, RL, +1>::run(v);
+#pragma unroll
+            for (int m = 0; m < RL; ++m) pp[m * NC] = v[m];
+            g = gn;
+        }
+        IP::template dit_butinner<T, +1, NC, NTHG>(sm, tw_s, gtid, bar);
+        fence_proxy_async();
+        mbar_arrive(done_bar(b));
+    }
+}
+
+// filter tables in middle-stage order: Fm[adj][q][tile][m][j][c] = S(ky,kx) * (adj ? conj(H) : H) / (2*Hp*Wp),
+// ky = kymap[j*RL + m]
+template <typename T>
+__global__ void k_gd_tile_filter_mid(const typename CxT<T>::type* __restrict__ H, const typename CxT<T>::type* __restrict__ Sy,
+                                     const typename CxT<T>::type* __restrict__ Sx, const int* __restrict__ kymap,
+                                     typename CxT<T>::type* __restrict__ F, int DC, int Hp, int Wp, int Nh, int NTg, int RL) {
+    using C = typename CxT<T>::type;
+    const int NBL = Hp / RL;
+    const int64_t n = (int64_t)DC * NTg * Hp * LPC_GNC;
+    const T scale = (T)(0.5 / ((double)Hp * (double)Wp));
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % LPC_GNC);
+        int64_t r = i / LPC_GNC;
+        const int mj = (int)(r % Hp); r /= Hp;
+        const int tile = (int)(r % NTg);
+        const int q = (int)(r / NTg);
+        const int m = mj / NBL, j = mj - m * NBL;
+        const int ky = kymap[j * RL + m];
+        const int kx = tile * LPC_GNC + c;
+        C fwd, adj;
+        fwd.x = fwd.y = adj.x = adj.y = T(0);
+        if (kx < Nh) {
+            C hq = H[((int64_t)q * Hp + ky) * Nh + kx];
+            const C S = cx_mul(Sy[ky], Sx[kx]);
+            fwd = cx_mul(S, hq);
+            hq.y = -hq.y;
+            adj = cx_mul(S, hq);
+            fwd.x *= scale; fwd.y *= scale; adj.x *= scale; adj.y *= scale;
+        }
+        F[i] = fwd;
+        F[n + i] = adj;
     }
 }
 
