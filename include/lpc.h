@@ -115,6 +115,19 @@ int lpc_set_admm_params(lpc_plan_t plan, double mu1, double mu2, double mu3, dou
 int lpc_set_gd_params(lpc_plan_t plan, double lip_fact, double nesterov_mu, double fista_tk,
                       void* stream);
 
+/* Unrolled solvers: per-iteration hyper-parameters (inference only, no autograd).
+ * ADMM: mu1[i], mu2[i], mu3[i], tau[i], i < n -- the |.| of UnrolledADMM's parameter vectors
+ * (unrolled_admm.py:80-99,141-144); iteration i of every lpc_run uses entry i (R_divmat and X_divmat of
+ * that iteration, unrolled_admm.py:166-179,181-234); n_iter <= n.  n == 0 restores the constant
+ * parameters of lpc_set_admm_params.
+ * FISTA: alpha[i*C + c] and tk[0..n] (unrolled_fista.py:60-83,102-106): x <- x - alpha_i grad,
+ * xk = proj(x), x = xk + (tk_i - 1)/tk_{i+1} (xk - xk_prev), with xk_prev initialised to the initial
+ * estimate (unrolled_fista.py:95-100; lensless.FISTA's first-iteration aliasing does not apply).
+ * The position advances across runs until lpc_reset.  Host arrays, copied. */
+int lpc_set_admm_schedule(lpc_plan_t plan, int n, const double* mu1, const double* mu2, const double* mu3,
+                          const double* tau, void* stream);
+int lpc_set_fista_schedule(lpc_plan_t plan, int n, const double* alpha, const double* tk, void* stream);
+
 /* ReconstructionAlgorithm.set_data (recon.py:352-381) + optional background
  * subtraction and clamp (recon.py:553-555; dev_background may be NULL).
  * dev_data is [B, Dd, h, w, C] with Dd in {1, D}; strides are ELEMENT strides

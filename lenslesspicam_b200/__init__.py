@@ -21,6 +21,8 @@ from .gd import (  # noqa: E402
     non_neg,
 )
 
+from .unrolled import UnrolledADMM, UnrolledFISTA  # noqa: E402
+
 __version__ = "0.1.0"
 __all__ = [
     "ADMM",
@@ -29,6 +31,8 @@ __all__ = [
     "GradientDescentUpdate",
     "NesterovGradientDescent",
     "RealFFTConvolve2D",
+    "UnrolledADMM",
+    "UnrolledFISTA",
     "ReconstructionAlgorithm",
     "apply_admm",
     "non_neg",

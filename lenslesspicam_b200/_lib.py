@@ -29,6 +29,7 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _d = ctypes.c_double
 _ip = ctypes.POINTER(ctypes.c_int)
+_dp = ctypes.POINTER(ctypes.c_double)
 _i64p = ctypes.POINTER(ctypes.c_int64)
 
 # name -> (restype, argtypes); must list every symbol include/lpc.h declares
@@ -43,6 +44,8 @@ PROTOTYPES = {
     "lpc_set_psf": (_i, [_vp, _vp, _vp]),
     "lpc_set_admm_params": (_i, [_vp, _d, _d, _d, _d, _vp]),
     "lpc_set_gd_params": (_i, [_vp, _d, _d, _d, _vp]),
+    "lpc_set_admm_schedule": (_i, [_vp, _i, _dp, _dp, _dp, _dp, _vp]),
+    "lpc_set_fista_schedule": (_i, [_vp, _i, _dp, _dp, _vp]),
     "lpc_set_data": (_i, [_vp, _vp, _i, _i64p, _vp, _i64p, _vp, _vp]),
     "lpc_set_data_host": (_i, [_vp, _vp, _i, _vp]),
     "lpc_reset": (_i, [_vp, _vp, _vp]),

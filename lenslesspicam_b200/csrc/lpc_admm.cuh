@@ -28,6 +28,8 @@ namespace lpc {
 template <typename T>
 struct AdmmK {
     T mu1, mu2, mu3, thr;     // thr = tau / mu2
+    T mu1p, mu2p, mu3p;       // the PREVIOUS iteration's mu: it completes the half-updated duals (equal to mu1..3
+                              // unless an unrolled per-iteration schedule is set, unrolled_admm.py:222-234)
     T inv_mu2, inv_mu3;       // reciprocals for the fused engine (FAST = true: x*(1/mu) instead of x/mu)
     T xdiv_in, xdiv_out;      // X_divmat inside / outside the sensor window (admm.py:193)
     int Hp, Wp;               // padded plane
@@ -50,7 +52,7 @@ template <typename T> __device__ __forceinline__ T soft_thresh(T z, T thr) {
 // FAST: multiply by the precomputed reciprocal instead of the IEEE division (<= 1 ulp apart)
 template <typename T, bool FAST = false>
 __device__ __forceinline__ T tv_component(T psi, T eta_half, const AdmmK<T>& k, T& eta_half_new) {
-    const T eta = eta_half + k.mu2 * psi;
+    const T eta = eta_half + k.mu2p * psi;
     const T u = soft_thresh(psi + (FAST ? eta * k.inv_mu2 : eta / k.mu2), k.thr);
     eta_half_new = eta - k.mu2 * u;
     return -eta_half_new;
@@ -59,10 +61,10 @@ __device__ __forceinline__ T tv_component(T psi, T eta_half, const AdmmK<T>& k, 
 template <typename T, bool FAST = false>
 __device__ __forceinline__ void point_update(T v, T hv, T y, bool in_window, T xi_half, T rho_half,
                                              const AdmmK<T>& k, T& xi_half_new, T& rho_half_new) {
-    const T xi = xi_half + k.mu1 * hv;
+    const T xi = xi_half + k.mu1p * hv;
     const T x = (in_window ? k.xdiv_in : k.xdiv_out) * (xi + k.mu1 * hv + y);
     xi_half_new = xi - k.mu1 * x;
-    const T rho = rho_half + k.mu3 * v;
+    const T rho = rho_half + k.mu3p * v;
     T w = (FAST ? rho * k.inv_mu3 : rho / k.mu3) + v;
     w = w > T(0) ? w : T(0);
     rho_half_new = rho - k.mu3 * w;

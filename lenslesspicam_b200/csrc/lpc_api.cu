@@ -116,6 +116,8 @@ struct lpc_plan_s {
     virtual int set_psf(const void*, cudaStream_t) = 0;
     virtual int set_admm_params(double, double, double, double, cudaStream_t) = 0;
     virtual int set_gd_params(double, double, double, cudaStream_t) = 0;
+    virtual int set_admm_schedule(int, const double*, const double*, const double*, const double*, cudaStream_t) = 0;
+    virtual int set_fista_schedule(int, const double*, const double*, cudaStream_t) = 0;
     virtual int set_data(const void*, int, const int64_t*, const void*, const int64_t*, void*, cudaStream_t) = 0;
     virtual int set_data_host(const void*, int, cudaStream_t) = 0;
     virtual int reset(const void*, cudaStream_t) = 0;
@@ -215,11 +217,20 @@ struct Plan : lpc_plan_s {
     size_t work_bytes = 0;
     // ---- parameters / flags
     double mu1 = 1e-6, mu2 = 1e-5, mu3 = 4e-5, tau = 1e-4;
+    // unrolled per-iteration parameters (unrolled_admm.py:181-234, unrolled_fista.py:102-106); empty = constant
+    std::vector<double> s_mu1, s_mu2, s_mu3, s_tau;   // ADMM: [n]
+    std::vector<double> s_tk;                          // FISTA: [n+1]
+    T* alpha_sched = nullptr;                          // FISTA: device [n][4C], alpha_c of iteration i at [i*4C + 3C + c]
+    size_t alpha_cap = 0;
+    int n_sched = 0;
+    double pm1 = 1e-6, pm2 = 1e-5, pm3 = 4e-5;         // mu of the last enqueued ADMM iteration: completes the half duals
+    int gd_it = 0;                                     // FISTA schedule position (iterations since reset)
     double lip = 1.8, nmu = 0.9, tk0 = 1.0, tk = 1.0;
     bool psf_set = false, data_set = false, state_ready = false, fista_first = true;
     // ---- graph cache (one entry)
     cudaGraphExec_t gexec = nullptr;
-    int g_niter = -1, g_eta = -1, g_first = -1, g_vh = -1;
+    int g_niter = -1, g_eta = -1, g_first = -1, g_vh = -1, g_gdit = -1;
+    double g_pm[3] = {0, 0, 0};
     double g_tk = 0;
     cudaStream_t g_stream = nullptr;
 
@@ -434,19 +445,19 @@ struct Plan : lpc_plan_s {
         }
         return LPC_OK;
     }
-    int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o, int p0 = 0, int np = -1, const T* vh = nullptr) {
+    int launch_rows_spatial(cudaStream_t st, const T* eta_i, T* eta_o, int p0 = 0, int np = -1, const T* vh = nullptr, int it = 0) {
         if constexpr (std::is_same<T, float>::value) {
             if (np < 0) np = Np;
             const int ry = 1 << ry_log2;
             dim3 grid((Hp + ry - 1) / ry, np);
             FusedK k = fk; k.plane0 = p0;
-            rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, admm_k(), tw_row, vh ? vh : VH, Tout, data,
+            rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, admm_k(it, true), tw_row, vh ? vh : VH, Tout, data,
                                                                           AX + (int64_t)Np * plane, rho, eta_i, eta_o);
             LPC_KCHECK();
         }
         return LPC_OK;
     }
-    int launch_cols(cudaStream_t st, int p0 = 0, int np = -1) {
+    int launch_cols(cudaStream_t st, int p0 = 0, int np = -1, int it = 0) {
         if constexpr (std::is_same<T, float>::value) {
             if (np < 0) np = Np;
             dim3 grid(fk.NT, np);
@@ -457,13 +468,16 @@ struct Plan : lpc_plan_s {
                 const int nblk = n_items < n_sms ? n_items : n_sms;
                 if constexpr (std::is_same<T, float>::value) {
                     ColsTmaK ck = ctk;
-                    ck.mu1 = (float)mu1; ck.mu2 = (float)mu2; ck.mu3 = (float)mu3;
+                    double m[4];
+                    admm_params(it, m);
+                    ck.mu1 = (float)m[0]; ck.mu2 = (float)m[1]; ck.mu3 = (float)m[2];
                     ck.scale = (float)(0.5 / ((double)Hp * (double)Wp));
                     cols_entry->tma[cols_tma - 1]<<<nblk, nthr, smem_cols_tma, st>>>(k, ck, n_items, tabs_ip, Tout, Tin, Hm, Gx, Sx);
                 }
                 LPC_KCHECK();
                 return LPC_OK;
             }
+            if (n_sched > 0) { int rc = compute_R(st, it); if (rc) return rc; }  // the R table of THIS iteration's mu
             cols_entry->kern[cols_variant]<<<grid, cols_variant ? 576 : 1024, smem_col, st>>>(k, tw_col, tw_col_rev, Tout, Tin, Ht, Rt, Sy, Sx);
             LPC_KCHECK();
         }
@@ -620,13 +634,13 @@ struct Plan : lpc_plan_s {
             return LPC_OK;
         }
     }
-    int gd2_rows(int mode, T scalar, int first, cudaStream_t st, int p0 = 0, int np = -1) {
+    int gd2_rows(int mode, T scalar, int first, cudaStream_t st, int p0 = 0, int np = -1, const T* cst = nullptr) {
         if constexpr (std::is_same<T, float>::value) {
             gk.Dd = Dd;
             if (np < 0) np = Np;
             dim3 grid((h + 1) / 2, np);
             GdFusedK k = gk; k.plane0 = p0;
-            rows_entry->gd[mode]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, tw_row_rev, Tg, data, xu, mom, consts, scalar, first);
+            rows_entry->gd[mode]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, tw_row_rev, Tg, data, xu, mom, cst ? cst : consts, scalar, first);
             LPC_KCHECK();
         }
         return LPC_OK;
@@ -649,6 +663,27 @@ struct Plan : lpc_plan_s {
         }
         return LPC_OK;
     }
+    // scalars of the next FISTA update: the t_k recursion of gd.py:238-239, or the next entry of an unrolled
+    // schedule (unrolled_fista.py:102-106: alpha[i][c], (t_i - 1)/t_{i+1}, no first-iteration aliasing)
+    struct FistaStep { T beta; int first; const T* consts; };
+    FistaStep fista_step() {
+        FistaStep f;
+        if (n_sched > 0) {
+            const int i = gd_it < n_sched ? gd_it : n_sched - 1;
+            f.beta = (T)((s_tk[i] - 1.0) / s_tk[i + 1]);
+            f.first = 0;
+            f.consts = alpha_sched + (size_t)i * 4 * C;
+            ++gd_it;
+        } else {
+            const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;  // gd.py:238
+            f.beta = (T)((tk - 1.0) / tn);
+            f.first = fista_first ? 1 : 0;
+            f.consts = consts;
+            tk = tn;
+            fista_first = false;
+        }
+        return f;
+    }
     int gd2_iteration(cudaStream_t st, cudaEvent_t* ev) {
 #define LPC_EV(i) do { if (ev) LPC_CK(cudaEventRecord(ev[i], st)); } while (0)
         int rc;
@@ -664,10 +699,8 @@ struct Plan : lpc_plan_s {
         } else if (algo == LPC_ALGO_NESTEROV) {
             rc = gd2_rows(LPC_GD_UPD_NESTEROV, (T)nmu, 0, st);
         } else {
-            const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;  // gd.py:238
-            rc = gd2_rows(LPC_GD_UPD_FISTA, (T)((tk - 1.0) / tn), fista_first ? 1 : 0, st);
-            tk = tn;
-            fista_first = false;
+            const FistaStep f = fista_step();
+            rc = gd2_rows(LPC_GD_UPD_FISTA, f.beta, f.first, st, 0, -1, f.consts);
         }
         if (rc) return rc;
         LPC_EV(4);
@@ -718,9 +751,22 @@ struct Plan : lpc_plan_s {
         return LPC_OK;
     }
 
-    AdmmK<T> admm_k() const {
+    // parameters of iteration `it` of a run (the schedule restarts at 0 with every lpc_run)
+    void admm_params(int it, double* m) const {
+        if (n_sched > 0 && algo == LPC_ALGO_ADMM) {
+            const int i = it < n_sched ? it : n_sched - 1;
+            m[0] = s_mu1[i]; m[1] = s_mu2[i]; m[2] = s_mu3[i]; m[3] = s_tau[i];
+        } else {
+            m[0] = mu1; m[1] = mu2; m[2] = mu3; m[3] = tau;
+        }
+    }
+    AdmmK<T> admm_k(int it = 0, bool use_prev = false) const {
+        double m[4];
+        admm_params(it, m);
+        const double mu1 = m[0], mu2 = m[1], mu3 = m[2], tau = m[3];
         AdmmK<T> k;
         k.mu1 = (T)mu1; k.mu2 = (T)mu2; k.mu3 = (T)mu3;
+        k.mu1p = use_prev ? (T)pm1 : k.mu1; k.mu2p = use_prev ? (T)pm2 : k.mu2; k.mu3p = use_prev ? (T)pm3 : k.mu3;
         k.thr = (T)(tau / mu2);
         k.inv_mu2 = T(1) / (T)mu2;
         k.inv_mu3 = T(1) / (T)mu3;
@@ -741,8 +787,10 @@ struct Plan : lpc_plan_s {
     }
 
     // ---------------------------------------------------------------- PSF
-    int compute_R(cudaStream_t st) {
-        k_admm_R<T><<<1184, 256, 0, st>>>(Hc, Rn, DC, Hp, Wp, Nh, mu1, mu2, mu3);
+    int compute_R(cudaStream_t st, int it = 0) {
+        double m[4];
+        admm_params(it, m);
+        k_admm_R<T><<<1184, 256, 0, st>>>(Hc, Rn, DC, Hp, Wp, Nh, m[0], m[1], m[2]);
         LPC_KCHECK();
         if (v2) return tile_HR(st);
         return LPC_OK;
@@ -815,6 +863,43 @@ struct Plan : lpc_plan_s {
         return LPC_OK;
     }
 
+    // unrolled per-iteration parameters; n == 0 clears the schedule
+    int set_admm_schedule(int n, const double* a, const double* b, const double* c, const double* d, cudaStream_t st) override {
+        if (algo != LPC_ALGO_ADMM) return fail(LPC_ESTATE, "set_admm_schedule", "not an ADMM plan");
+        if (n < 0 || (n > 0 && (!a || !b || !c || !d))) return fail(LPC_EINVAL, "set_admm_schedule", "bad arguments");
+        for (int i = 0; i < n; ++i)
+            if (!(a[i] > 0) || !(b[i] > 0) || !(c[i] > 0)) return fail(LPC_EINVAL, "set_admm_schedule", "mu must be > 0");
+        LPC_CK(cudaSetDevice(device));
+        drop_graph();
+        s_mu1.assign(a, a + n); s_mu2.assign(b, b + n); s_mu3.assign(c, c + n); s_tau.assign(d, d + n);
+        n_sched = n;
+        { double m[4]; admm_params(0, m); pm1 = m[0]; pm2 = m[1]; pm3 = m[2]; }
+        if (n == 0 && psf_set) return compute_R(st);  // back to the constant-parameter table
+        return LPC_OK;
+    }
+    int set_fista_schedule(int n, const double* alpha, const double* tks, cudaStream_t st) override {
+        if (algo != LPC_ALGO_FISTA) return fail(LPC_ESTATE, "set_fista_schedule", "not a FISTA plan");
+        if (n < 0 || (n > 0 && (!alpha || !tks))) return fail(LPC_EINVAL, "set_fista_schedule", "bad arguments");
+        LPC_CK(cudaSetDevice(device));
+        drop_graph();
+        n_sched = 0;
+        state_ready = false;  // the previous-iterate convention differs: reset before the next run
+        if (n == 0) return LPC_OK;
+        std::vector<T> tab((size_t)n * 4 * C, T(0));
+        for (int i = 0; i < n; ++i)
+            for (int c = 0; c < C; ++c) tab[(size_t)i * 4 * C + 3 * C + c] = (T)alpha[(size_t)i * C + c];
+        if (tab.size() > alpha_cap) {  // (an outgrown table is released with the plan)
+            int rc = alloc(&alpha_sched, tab.size());
+            if (rc) return rc;
+            alpha_cap = tab.size();
+        }
+        LPC_CK(cudaMemcpyAsync(alpha_sched, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        LPC_CK(cudaStreamSynchronize(st));  // `tab` is a pageable host temporary
+        s_tk.assign(tks, tks + n + 1);
+        n_sched = n;
+        return LPC_OK;
+    }
+
     // ---------------------------------------------------------------- data
     int set_data(const void* dev_data, int Dd_in, const int64_t* strides, const void* dev_bg,
                  const int64_t* bg_strides, void* dev_echo, cudaStream_t st) override {
@@ -884,6 +969,7 @@ struct Plan : lpc_plan_s {
             LPC_CK(cudaMemsetAsync(rho, 0, (size_t)Np * plane * sizeof(T), st));
             LPC_CK(cudaMemsetAsync(eta[0], 0, (size_t)2 * Np * plane * sizeof(T), st));
             eta_cur = 0;
+            { double m[4]; admm_params(0, m); pm1 = m[0]; pm2 = m[1]; pm3 = m[2]; }
             if (v2) {
                 LPC_CK(cudaMemsetAsync(Tin, 0, (size_t)Np * fk.NT * Hp * 2 * LPC_NCT * sizeof(Cplx), st));
                 vh_valid = true;  // V = HV = 0 sits in VH
@@ -928,6 +1014,12 @@ struct Plan : lpc_plan_s {
             }
             if (gd2 && (rc = gd2_rows(LPC_GD_INIT, T(0), 0, st))) return rc;  // row spectra of the initial estimate
             if (mom) LPC_CK(cudaMemsetAsync(mom, 0, (size_t)Np * h * w * sizeof(T), st));
+            if (n_sched > 0 && algo == LPC_ALGO_FISTA) {
+                // unrolled_fista.py:95-100: the previous iterate starts as the initial estimate itself
+                if (!gd2) return fail(LPC_ENOTIMPL, "reset", "unrolled FISTA schedules need the fused engine (fp32, menu sizes)");
+                LPC_CK(cudaMemcpyAsync(mom, xu, (size_t)Np * h * w * sizeof(T), cudaMemcpyDeviceToDevice, st));
+            }
+            gd_it = 0;
             tk = tk0;            // gd.py:227-233
             fista_first = true;  // xk aliases x right after reset (gd.py:233)
         }
@@ -937,22 +1029,30 @@ struct Plan : lpc_plan_s {
 
     // ---------------------------------------------------------------- iterations
     // ev (optional): n_phases+1 events recorded at the phase boundaries (lpc_profile)
-    int admm_iteration(cudaStream_t st, cudaEvent_t* ev = nullptr) {
+    // bookkeeping after iteration `it` has been enqueued: its mu completes the next iteration's half duals
+    void admm_advance(int it) {
+        double m[4];
+        admm_params(it, m);
+        pm1 = m[0]; pm2 = m[1]; pm3 = m[2];
+    }
+    int admm_iteration(cudaStream_t st, cudaEvent_t* ev = nullptr, int it = 0) {
 #define LPC_EV(i) do { if (ev) LPC_CK(cudaEventRecord(ev[i], st)); } while (0)
         LPC_EV(0);
         if (v2) {
             int rc = materialise_vh(st);  // B1: row IFFT -> V, HV (skipped when VH already holds them, e.g. after reset)
             if (rc) return rc;
             LPC_EV(1);
-            if ((rc = launch_rows_spatial(st, eta[eta_cur], eta[eta_cur ^ 1]))) return rc;  // B2
+            if ((rc = launch_rows_spatial(st, eta[eta_cur], eta[eta_cur ^ 1], 0, -1, nullptr, it))) return rc;  // B2
             eta_cur ^= 1;
             vh_valid = false;
             LPC_EV(2);
-            if ((rc = launch_cols(st))) return rc;  // A
+            if ((rc = launch_cols(st, 0, -1, it))) return rc;  // A
             LPC_EV(3);
+            admm_advance(it);
             return LPC_OK;
         }
-        const AdmmK<T> k = admm_k();
+        const AdmmK<T> k = admm_k(it, true);
+        if (n_sched > 0) { int rc = compute_R(st, it); if (rc) return rc; }
         T* a = AX;
         T* xi = AX + (int64_t)Np * plane;
         const T* V = VH;
@@ -978,6 +1078,7 @@ struct Plan : lpc_plan_s {
         LPC_EV(3);
         LPC_CF(FftTraits<T>::inv(inv, spec, VH));
         LPC_EV(4);
+        admm_advance(it);
         return LPC_OK;
     }
 
@@ -1010,11 +1111,8 @@ struct Plan : lpc_plan_s {
             k_nesterov_update<T><<<grid, 128, 0, st>>>(k, rpad, consts, xpad, mom, (T)nmu);
         } else {
             // gd.py:238-240: t_{k+1} = (1 + sqrt(1 + 4 t_k^2))/2 ; beta = (t_k - 1)/t_{k+1}
-            const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
-            const T beta = (T)((tk - 1.0) / tn);
-            k_fista_update<T><<<grid, 128, 0, st>>>(k, rpad, consts, xpad, mom, beta, fista_first ? 1 : 0);
-            tk = tn;
-            fista_first = false;
+            const FistaStep f = fista_step();
+            k_fista_update<T><<<grid, 128, 0, st>>>(k, rpad, f.consts, xpad, mom, f.beta, f.first);
         }
         LPC_KCHECK();
         LPC_EV(8);
@@ -1066,16 +1164,14 @@ struct Plan : lpc_plan_s {
         for (int c = 1; c < n_chains; ++c) LPC_CK(cudaStreamWaitEvent(side[c], ev_fork, 0));
         for (int it = 0; it < n_iter; ++it) {
             T scalar = T(0);
+            const T* cst = nullptr;
             int first = 0, upd_mode = LPC_GD_UPD_GD;
             if (gd2) {
                 if (algo == LPC_ALGO_NESTEROV) { scalar = (T)nmu; upd_mode = LPC_GD_UPD_NESTEROV; }
                 if (algo == LPC_ALGO_FISTA) {
-                    const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;  // gd.py:238
-                    scalar = (T)((tk - 1.0) / tn);
-                    first = fista_first ? 1 : 0;
+                    const FistaStep f = fista_step();
+                    scalar = f.beta; first = f.first; cst = f.consts;
                     upd_mode = LPC_GD_UPD_FISTA;
-                    tk = tn;
-                    fista_first = false;
                 }
             }
             for (int c = 0; c < n_chains; ++c) {
@@ -1084,16 +1180,16 @@ struct Plan : lpc_plan_s {
                 chain_range(c, &p0, &np);
                 if (v2) {
                     if (!vh_valid && (rc = launch_rows_ifft(cs, p0, np))) return rc;
-                    if ((rc = launch_rows_spatial(cs, eta[eta_cur], eta[eta_cur ^ 1], p0, np))) return rc;
-                    if ((rc = launch_cols(cs, p0, np))) return rc;
+                    if ((rc = launch_rows_spatial(cs, eta[eta_cur], eta[eta_cur ^ 1], p0, np, nullptr, it))) return rc;
+                    if ((rc = launch_cols(cs, p0, np, it))) return rc;
                 } else {
                     if ((rc = gd2_cols(0, cs, p0, np))) return rc;
                     if ((rc = gd2_rows(LPC_GD_RESID, T(0), 0, cs, p0, np))) return rc;
                     if ((rc = gd2_cols(1, cs, p0, np))) return rc;
-                    if ((rc = gd2_rows(upd_mode, scalar, first, cs, p0, np))) return rc;
+                    if ((rc = gd2_rows(upd_mode, scalar, first, cs, p0, np, cst))) return rc;
                 }
             }
-            if (v2) { eta_cur ^= 1; vh_valid = false; }
+            if (v2) { eta_cur ^= 1; vh_valid = false; admm_advance(it); }
         }
         for (int c = 1; c < n_chains; ++c) {
             LPC_CK(cudaEventRecord(ev_join[c], side[c]));
@@ -1110,13 +1206,16 @@ struct Plan : lpc_plan_s {
     int iterate_plane_major(int n_iter, cudaStream_t st) {
         int rc = LPC_OK;
         const int eta0 = eta_cur;
+        const double q1 = pm1, q2 = pm2, q3 = pm3;
         for (int p = 0; p < Np; ++p) {
             T* vh = vh_shared ? VH - (int64_t)p * plane : VH;  // plane p of this view is plane 0 of VH (V) / of its HV half
+            pm1 = q1; pm2 = q2; pm3 = q3;
             for (int it = 0; it < n_iter; ++it) {
                 const int ei = (eta0 + it) & 1;
                 if ((rc = launch_rows_ifft(st, p, 1, vh))) return rc;
-                if ((rc = launch_rows_spatial(st, eta[ei], eta[ei ^ 1], p, 1, vh))) return rc;
-                if ((rc = launch_cols(st, p, 1))) return rc;
+                if ((rc = launch_rows_spatial(st, eta[ei], eta[ei ^ 1], p, 1, vh, it))) return rc;
+                if ((rc = launch_cols(st, p, 1, it))) return rc;
+                admm_advance(it);
             }
         }
         eta_cur = (eta0 + n_iter) & 1;
@@ -1128,7 +1227,7 @@ struct Plan : lpc_plan_s {
         if (v2 && plane_major && n_chains == 1) return iterate_plane_major(n_iter, st);
         if ((v2 || gd2) && n_chains > 1) return iterate_chains(n_iter, st);
         int rc = LPC_OK;
-        for (int i = 0; i < n_iter && rc == LPC_OK; ++i) rc = (algo == LPC_ALGO_ADMM) ? admm_iteration(st) : gd_iteration(st);
+        for (int i = 0; i < n_iter && rc == LPC_OK; ++i) rc = (algo == LPC_ALGO_ADMM) ? admm_iteration(st, nullptr, i) : gd_iteration(st);
         return rc;
     }
 
@@ -1138,6 +1237,10 @@ struct Plan : lpc_plan_s {
         if (!state_ready) return fail(LPC_ESTATE, "run", "call lpc_reset first");
         if (n_iter < 0) return fail(LPC_EINVAL, "run", "n_iter < 0");
         if (n_iter == 0) return LPC_OK;
+        if (n_sched > 0 && algo == LPC_ALGO_ADMM && n_iter > n_sched)
+            return fail(LPC_EINVAL, "run", "n_iter exceeds the unrolled schedule (the schedule restarts at 0 with every run)");
+        if (n_sched > 0 && algo == LPC_ALGO_FISTA && gd_it + n_iter > n_sched)
+            return fail(LPC_EINVAL, "run", "iterations since reset exceed the unrolled schedule");
         LPC_CK(cudaSetDevice(device));
         if (have_fwd) LPC_CF(cufftSetStream(fwd, st));
         if (have_inv) LPC_CF(cufftSetStream(inv, st));
@@ -1148,11 +1251,12 @@ struct Plan : lpc_plan_s {
         const int first = fista_first ? 1 : 0;
         const int vh0 = vh_valid ? 1 : 0;  // the first captured iteration skips B1 when VH already holds V, HV
         const bool hit = gexec && g_niter == n_iter && g_eta == eta_cur && g_stream == st && g_vh == vh0 &&
-                         (algo != LPC_ALGO_FISTA || (g_tk == tk && g_first == first));
+                         (algo != LPC_ALGO_FISTA || (g_tk == tk && g_first == first && g_gdit == gd_it)) &&
+                         (algo != LPC_ALGO_ADMM || (g_pm[0] == pm1 && g_pm[1] == pm2 && g_pm[2] == pm3));
         if (!hit) {
             drop_graph();
-            const int eta0 = eta_cur;
-            const double tk_start = tk;
+            const int eta0 = eta_cur, gdit0 = gd_it;
+            const double tk_start = tk, pm0[3] = {pm1, pm2, pm3};
             cudaGraph_t graph = nullptr;
             LPC_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             int rc = iterate(n_iter, st);
@@ -1163,12 +1267,14 @@ struct Plan : lpc_plan_s {
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { gexec = nullptr; return fail(LPC_ECUDA, "cudaGraphInstantiate", cudaGetErrorString(e)); }
             g_niter = n_iter; g_eta = eta0; g_tk = tk_start; g_first = first; g_stream = st; g_vh = vh0;
+            g_gdit = gdit0; g_pm[0] = pm0[0]; g_pm[1] = pm0[1]; g_pm[2] = pm0[2];
             // iterate() advanced the host-side bookkeeping while capturing; nothing ran yet
         } else {
             // replay: advance the host-side bookkeeping exactly as iterate() would
-            if (algo == LPC_ALGO_ADMM) eta_cur ^= (n_iter & 1);
+            if (algo == LPC_ALGO_ADMM) { eta_cur ^= (n_iter & 1); admm_advance(n_iter - 1); }
             if (algo == LPC_ALGO_FISTA) {
-                for (int i = 0; i < n_iter; ++i) tk = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
+                if (n_sched > 0) gd_it += n_iter;
+                else for (int i = 0; i < n_iter; ++i) tk = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;
                 fista_first = false;
             }
         }
@@ -1375,6 +1481,15 @@ int lpc_set_admm_params(lpc_plan_t plan, double mu1, double mu2, double mu3, dou
 int lpc_set_gd_params(lpc_plan_t plan, double lip_fact, double nesterov_mu, double fista_tk, void* stream) {
     LPC_NEED(plan);
     return plan->set_gd_params(lip_fact, nesterov_mu, fista_tk, (cudaStream_t)stream);
+}
+int lpc_set_admm_schedule(lpc_plan_t plan, int n, const double* mu1, const double* mu2, const double* mu3,
+                          const double* tau, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_admm_schedule(n, mu1, mu2, mu3, tau, (cudaStream_t)stream);
+}
+int lpc_set_fista_schedule(lpc_plan_t plan, int n, const double* alpha, const double* tk, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_fista_schedule(n, alpha, tk, (cudaStream_t)stream);
 }
 int lpc_set_data(lpc_plan_t plan, const void* dev_data, int Dd, const int64_t* strides, const void* dev_background,
                  const int64_t* bg_strides, void* dev_echo, void* stream) {

@@ -439,7 +439,78 @@ class OracleFISTA(OracleGD):
         self.xk = xk
 
 
+# ----------------------------------------------------------------------------
+# Unrolled solvers, inference path (unrolled_admm.py:20-251, unrolled_fista.py:19-106)
+# ----------------------------------------------------------------------------
+
+
+class OracleUnrolledADMM(OracleADMM):
+    """``lensless.UnrolledADMM.forward`` for one sample: ADMM whose mu1/mu2/mu3/tau have one entry per
+    iteration (|.| of the parameter vectors, unrolled_admm.py:141-144), with R_divmat / X_divmat of
+    that iteration (unrolled_admm.py:166-179) and the update order of unrolled_admm.py:222-234."""
+
+    def __init__(self, psf, dtype=None, n_iter=5, mu1=1e-6, mu2=1e-5, mu3=4e-5, tau=0.0001, workers=None):
+        def vec(v):
+            a = np.abs(np.asarray(v, dtype=np.float64))
+            return np.full((n_iter,), float(a)) if a.ndim == 0 else a
+
+        self.s_mu1, self.s_mu2, self.s_mu3, self.s_tau = vec(mu1), vec(mu2), vec(mu3), vec(tau)
+        super().__init__(psf, dtype=dtype, n_iter=n_iter, workers=workers)
+
+    def reset(self):
+        self.it = 0
+        self._set_iter(0)
+        super().reset()
+
+    def _set_iter(self, i):
+        dt = self.dtype
+        self.mu1, self.mu2, self.mu3, self.tau = (dt(v[i]) for v in (self.s_mu1, self.s_mu2, self.s_mu3, self.s_tau))
+
+    def update(self):
+        c = self.conv
+        self._set_iter(self.it)
+        # unrolled_admm.py:166-179: per-iteration division matrices
+        self.R = 1.0 / (self.mu1 * np.abs(c.Hadj * c.H) + self.mu2 * np.abs(self.PsiTPsi) + self.mu3).astype(self.cdtype)
+        self.Xdiv = 1.0 / (c.pad_to(np.ones(self.psf.shape, dtype=self.dtype)) + self.mu1)
+        super().update()
+        self.it += 1
+
+
+class OracleUnrolledFISTA(OracleGD):
+    """``lensless.UnrolledFISTA.forward`` for one sample (unrolled_fista.py:84-106): out-of-place step with
+    alpha[i][c], xk = proj(x), x = xk + (tk[i]-1)/tk[i+1] (xk - xk_prev); xk_prev starts as the initial estimate."""
+
+    def __init__(self, psf, dtype=None, n_iter=5, alpha=None, tk=1.0, workers=None):
+        self.s_alpha = None if alpha is None else np.abs(np.asarray(alpha, dtype=np.float64))
+        tks = np.asarray(tk, dtype=np.float64)
+        if tks.ndim == 0:
+            t = [float(tks)]
+            for i in range(n_iter):
+                t.append((1 + math.sqrt(1 + 4 * t[i] ** 2)) / 2)
+            tks = np.asarray(t)
+        self.s_tk = np.abs(tks)
+        super().__init__(psf, dtype=dtype, lip_fact=1.8, n_iter=n_iter, workers=workers)
+
+    def reset(self):
+        super().reset()
+        if self.s_alpha is None:  # unrolled_fista.py:60-73: every iteration starts from 1.8 / max|H*H|
+            self.s_alpha = np.tile(self.alpha.astype(np.float64)[None, :], (self.n_iter, 1))
+        self.it = 0
+        self.xk = self.x
+
+    def update(self):
+        i = self.it
+        a = self.s_alpha[i].astype(self.dtype)
+        self.x = self.x - a * self.grad()
+        xk = self.proj(self.x)
+        self.x = xk + self.dtype((self.s_tk[i] - 1) / self.s_tk[i + 1]) * (xk - self.xk)
+        self.xk = xk
+        self.it += 1
+
+
 ALGOS = {
+    "unrolled_admm": OracleUnrolledADMM,
+    "unrolled_fista": OracleUnrolledFISTA,
     "admm": OracleADMM,
     "gd": OracleGD,
     "nesterov": OracleNesterov,

@@ -21,6 +21,8 @@ Fixtures (all float32 inputs, seeded):
 * ``convolver``        RealFFTConvolve2D pad/crop/convolve/deconvolve on the
                        reference test's shapes (PSF 5x47x29x3, data 2x5x47x29x3 (the reference test uses batch 12); test_convolver.py:11-59)
 * ``batch``            UnrolledADMM.forward(batch) == per-sample ADMM
+* ``unrolled``         UnrolledADMM / UnrolledFISTA .forward(batch) with per-iteration parameters
+                       (``python tests/golden/make_golden.py --only-unrolled`` regenerates just this one)
 
 Each npz stores inputs and, per algorithm/iteration count, the reference's
 torch-fp32 output (``t32``: the parity target), its numpy-fp32 output (``n32``)
@@ -103,9 +105,52 @@ def make_case(lensless, torch, fname, psf, data, iters):
     print("wrote", fname, {k: v.shape for k, v in store.items() if k in ("psf", "data")})
 
 
+def make_unrolled(lensless, torch):
+    """``unrolled.npz``: UnrolledADMM / UnrolledFISTA .forward(batch) with DIFFERENT parameters per iteration
+    (unrolled_admm.py:80-99,181-234; unrolled_fista.py:60-83,102-106), torch fp32 and fp64, no_grad."""
+    psf, _ = synth(24, 32, 3, 9)
+    batch = np.stack([synth(24, 32, 3, 200 + b)[1] for b in range(3)])  # [3,1,24,32,3]
+    n = 6
+    rng = np.random.default_rng(99)
+    mu1 = 1e-6 * (0.5 + rng.random(n) * 2)
+    mu2 = 1e-5 * (0.5 + rng.random(n) * 2)
+    mu3 = 4e-5 * (0.5 + rng.random(n) * 2)
+    tau = 1e-4 * (0.5 + rng.random(n) * 2)
+    store = {"psf": psf, "batch": batch, "mu1": mu1, "mu2": mu2, "mu3": mu3, "tau": tau}
+    with torch.no_grad():
+        for tag, tdt, sdt in (("t32", torch.float32, "float32"), ("t64", torch.float64, "float64")):
+            un = lensless.UnrolledADMM(torch.from_numpy(psf).to(tdt), dtype=sdt, n_iter=n)
+            un._mu1_p = torch.nn.Parameter(torch.from_numpy(mu1).to(tdt))
+            un._mu2_p = torch.nn.Parameter(torch.from_numpy(mu2).to(tdt))
+            un._mu3_p = torch.nn.Parameter(torch.from_numpy(mu3).to(tdt))
+            un._tau_p = torch.nn.Parameter(torch.from_numpy(tau).to(tdt))
+            store[f"unrolled_admm_{tag}"] = un.forward(torch.from_numpy(batch).to(tdt)).numpy().copy()
+        # FISTA: perturbed step sizes per iteration and channel, a non-default momentum schedule
+        un = lensless.UnrolledFISTA(torch.from_numpy(psf), n_iter=n, tk=1.5)
+        alpha0 = un._alpha_p.detach().numpy().astype(np.float64)  # [n, C] = 1.8 / max|H*H|
+        alpha = alpha0 * (0.6 + 0.5 * rng.random(alpha0.shape))
+        tk = un._tk_p.detach().numpy().astype(np.float64) * (0.9 + 0.2 * rng.random(n + 1))
+        store["alpha"] = alpha
+        store["tk"] = tk
+        for tag, tdt, sdt in (("t32", torch.float32, "float32"), ("t64", torch.float64, "float64")):
+            un = lensless.UnrolledFISTA(torch.from_numpy(psf).to(tdt), dtype=sdt, n_iter=n, tk=1.5)
+            un._alpha_p = torch.nn.Parameter(torch.from_numpy(alpha).to(tdt))
+            un._tk_p = torch.nn.Parameter(torch.from_numpy(tk).to(tdt))
+            store[f"unrolled_fista_{tag}"] = un.forward(torch.from_numpy(batch).to(tdt)).numpy().copy()
+        # defaults (constant parameters): must equal ADMM / a FISTA without the first-iteration aliasing
+        un = lensless.UnrolledFISTA(torch.from_numpy(psf), n_iter=n)
+        store["unrolled_fista_default_t32"] = un.forward(torch.from_numpy(batch)).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "unrolled.npz"), **store)
+    print("wrote unrolled.npz", {k: v.shape for k, v in store.items()})
+
+
 def main():
     lensless = _import_reference()
     import torch
+
+    if "--only-unrolled" in sys.argv:
+        torch.manual_seed(0)
+        return make_unrolled(lensless, torch)
 
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -194,6 +239,8 @@ def main():
     store["admm_t32_10"] = np.stack(per)
     np.savez_compressed(os.path.join(HERE, "batch.npz"), **store)
     print("wrote batch.npz")
+
+    make_unrolled(lensless, torch)
 
     # ---- bundled data through the reference's own loader (config 1 inputs)
     from lensless.utils.io import load_data

@@ -372,3 +372,62 @@ def test_full_size_admm_against_oracle_and_properties():
     rec.set_data(dev(data))
     assert torch.equal(rec.apply(n_iter=10, disp_iter=None), full)  # reproducible after a batch-2 detour
     assert rel_to_max(both[0].cpu().numpy(), full.cpu().numpy()) <= 1e-6  # batch == single
+
+
+# ------------------------------------------------------------------------------ unrolled solvers
+def test_unrolled_admm_forward_matches_reference():
+    """UnrolledADMM.forward(batch) with a DIFFERENT (mu1, mu2, mu3, tau) per iteration against the reference's
+    own output (tests/golden/unrolled.npz) -- fused engine, cuFFT engine, graph replay, per-sample == batch."""
+    g = load_golden("unrolled")
+    n = len(g["mu1"])
+    kw = dict(n_iter=n, mu1=g["mu1"], mu2=g["mu2"], mu3=g["mu3"], tau=g["tau"])
+    batch = dev(g["batch"])
+    for engine in (None, "v1"):
+        rec = L().UnrolledADMM(dev(g["psf"]), engine=engine, **kw) if engine else L().UnrolledADMM(dev(g["psf"]), **kw)
+        out = rec.forward(batch)
+        assert tuple(out.shape) == g["unrolled_admm_t32"].shape
+        assert rel_to_max(out.cpu().numpy(), g["unrolled_admm_t32"]) <= TOL, engine
+        again = rec.forward(batch)  # CUDA-graph replay with the schedule baked in
+        assert torch.equal(out, again)
+        one = rec.forward(batch[1:2])
+        assert rel_to_max(one.cpu().numpy(), g["unrolled_admm_t32"][1:2]) <= TOL
+    # a live oracle run at a mid-size shape (TMA column kernel: R evaluated from this iteration's mu)
+    psf, data = orc.synthetic_problem(135, 240, 3, seed=21)
+    rec = L().UnrolledADMM(dev(psf), **kw)
+    out = rec.forward(dev(data)[None] if data.ndim == 4 else dev(data))
+    ref = orc.reconstruct("unrolled_admm", psf, data, n, mu1=g["mu1"], mu2=g["mu2"], mu3=g["mu3"], tau=g["tau"])
+    assert rel_to_max(out[0].cpu().numpy(), ref) <= TOL
+
+
+def test_unrolled_admm_constant_parameters_equal_admm():
+    g = load_golden("small_even_rgb")
+    a, _ = run("admm", g["psf"], g["data"], 7)
+    rec = L().UnrolledADMM(dev(g["psf"]), n_iter=7)
+    b = rec.forward(dev(g["data"])[None] if g["data"].ndim == 4 else dev(g["data"]))
+    assert torch.equal(a, b[0])
+
+
+def test_unrolled_fista_forward_matches_reference():
+    g = load_golden("unrolled")
+    n = g["alpha"].shape[0]
+    batch = dev(g["batch"])
+    rec = L().UnrolledFISTA(dev(g["psf"]), n_iter=n, tk=1.5)
+    rec.set_parameters(alpha=g["alpha"], tk=g["tk"])
+    out = rec.forward(batch)
+    assert rel_to_max(out.cpu().numpy(), g["unrolled_fista_t32"]) <= TOL
+    assert torch.equal(out, rec.forward(batch))
+    rec = L().UnrolledFISTA(dev(g["psf"]), n_iter=n)  # default steps 1.8 / max|H*H|, default tk recursion
+    out = rec.forward(batch)
+    assert rel_to_max(out.cpu().numpy(), g["unrolled_fista_default_t32"]) <= TOL
+
+
+def test_unrolled_rejects_processors_and_long_runs():
+    g = load_golden("unrolled")
+    with pytest.raises(NotImplementedError):
+        L().UnrolledADMM(dev(g["psf"]), n_iter=3, pre_process=lambda x: x)
+    rec = L().UnrolledADMM(dev(g["psf"]), n_iter=3)
+    rec.set_data(dev(g["batch"][0]))
+    from lenslesspicam_b200._lib import LpcError
+
+    with pytest.raises(LpcError):
+        rec.apply(n_iter=4, disp_iter=None, plot=False)  # more iterations than schedule entries

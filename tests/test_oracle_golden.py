@@ -112,3 +112,23 @@ def test_oracle_batch_equals_unrolled():
     outs = np.stack([orc.reconstruct("admm", g["psf"], g["batch"][b], 10) for b in range(4)])
     assert rel_to_max(outs, g["admm_t32_10"]) <= 1e-5
     assert rel_to_max(outs, g["unrolled_admm_t32_10"][:, :, :, :, :].reshape(outs.shape)) <= 1e-5
+
+
+def test_oracle_unrolled_matches_reference():
+    """UnrolledADMM / UnrolledFISTA .forward(batch) of the reference with per-iteration parameters
+    (tests/golden/unrolled.npz) vs the oracle's per-sample restatement."""
+    g = load_golden("unrolled")
+    n = len(g["mu1"])
+    for b in range(g["batch"].shape[0]):
+        out = orc.reconstruct("unrolled_admm", g["psf"], g["batch"][b], n, mu1=g["mu1"], mu2=g["mu2"], mu3=g["mu3"], tau=g["tau"])
+        assert rel_to_max(out, g["unrolled_admm_t32"][b]) <= 1e-5, b
+        out = orc.reconstruct("unrolled_fista", g["psf"], g["batch"][b], n, alpha=g["alpha"], tk=g["tk"])
+        assert rel_to_max(out, g["unrolled_fista_t32"][b]) <= 1e-5, b
+        out = orc.reconstruct("unrolled_fista", g["psf"], g["batch"][b], n)
+        assert rel_to_max(out, g["unrolled_fista_default_t32"][b]) <= 1e-5, b
+    out = orc.reconstruct("unrolled_admm", g["psf"].astype(np.float64), g["batch"][0].astype(np.float64), n, dtype="float64",
+                          mu1=g["mu1"], mu2=g["mu2"], mu3=g["mu3"], tau=g["tau"])
+    assert rel_to_max(out, g["unrolled_admm_t64"][0]) <= 1e-10
+    out = orc.reconstruct("unrolled_fista", g["psf"].astype(np.float64), g["batch"][0].astype(np.float64), n, dtype="float64",
+                          alpha=g["alpha"], tk=g["tk"])
+    assert rel_to_max(out, g["unrolled_fista_t64"][0]) <= 1e-10
