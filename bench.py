@@ -16,8 +16,9 @@ value     : whole-job recon/s with the measurement already resident in HBM (devi
             CUDA events, max over ranks).
 e2e       : same metric through the host-buffer call (pinned host measurement -> H2D ->
             recon -> D2H image) with the copies inside the timed region.
-roofline  : our dominant kernel (the fused ADMM spatial pass K1), algorithmic bytes / CUDA-event
-            duration measured live via lpc_profile(), against MEASURED_PEAKS.json.
+roofline  : our dominant kernel (the longest launch of the iteration: the fused spatial-update + row-FFT
+            kernel B2), algorithmic bytes / CUDA-event duration measured live via lpc_profile(),
+            against MEASURED_PEAKS.json.
 cpu_baseline : the numpy oracle port of the reference, timed on this box's host cores on a
             bounded sample (a few iterations at full size, scaled to 100).
 """
@@ -306,7 +307,7 @@ def main():
         "admm_spectral(K2)": 5.5 * Sp,           # v1: reads A,Xi,H,R; writes Vhat,HVhat
         "rows_ifft(B1)": 2.0 * Sp + 2.0 * P,             # v2: reads Tin(2Sp); writes V,HV
         "rows_spatial_fft(B2)": 10.0 * P + 2.0 * Sp + d,  # v2: reads V,HV,xi',rho',eta'(2P) (+y); writes xi',rho',eta'(2P),Tout(2Sp)
-        "admm_cols(A)": 5.5 * Sp,                # v2: reads Tout(2Sp),H,R; writes Tin(2Sp)
+        "admm_cols(A)": 5.0 * Sp,                # v2: reads Tout(2Sp),H; writes Tin(2Sp)  (R is evaluated on the fly)
         "update": 5.0 * d, "residual": 3.0 * d, "spec_mul_H": 3.0 * Sp, "spec_mul_Hadj": 3.0 * Sp,
     }
     # fused GD engine: G-layout buffer (window rows only) and the filter table, per launch

@@ -1198,11 +1198,13 @@ struct Plan : lpc_plan_s {
         return LPC_OK;
     }
 
-    // Plane-major order (fused ADMM engine): the planes of a plan are independent problems, so plane p runs ALL its
-    // iterations before plane p+1 starts.  Every producer -> consumer hand-off (A -> B1 through Tin, B1 -> B2 through
-    // V/HV, B2 -> A through Tout) is then 66 MB written and immediately read back, inside the 126 MB L2, instead of
-    // 3 x 66 MB with the other planes' traffic in between; V/HV of every plane share ONE scratch plane pair.
-    int plane_major = 1, vh_shared = 1;
+    // Plane-major order (fused ADMM engine, EXPERIMENT, off by default): the planes of a plan are independent
+    // problems, so plane p could run ALL its iterations before plane p+1 starts; every producer -> consumer hand-off
+    // (A -> B1 through Tin, B1 -> B2 through V/HV, B2 -> A through Tout) is then 66 MB written and immediately read
+    // back, inside the 126 MB L2, and V/HV of every plane share ONE scratch plane pair.  MEASURED slower on B200
+    // (0.533 vs 0.490 ms per iteration): the per-plane kernels lose ~13 % to partial waves and pipeline prologues
+    // (A 3 x 58 us vs 142 us), the L2 hand-off wins back ~4 %.  LPC_PLANE_MAJOR=1 enables it.
+    int plane_major = 0, vh_shared = 1;
     int iterate_plane_major(int n_iter, cudaStream_t st) {
         int rc = LPC_OK;
         const int eta0 = eta_cur;
