@@ -125,7 +125,7 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------- reference arm
-def run_reference(args):
+def run_reference(args, out):
     """The reference's own CPU implementation of the path: the numpy oracle port (the reference is
     pure Python and cannot travel to the GPU box), all host threads given to pocketfft.
     One step = ONE full-size iteration (a bounded sample); value scales it to n_iter."""
@@ -166,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 def cpu_baseline(args, n_iter):
@@ -197,11 +197,27 @@ def cpu_baseline(args, n_iter):
     }
 
 
+# ----------------------------------------------------------------------------------------- stdout hygiene
+class OneLineStdout:
+    """Rank 0 must print exactly ONE JSON line.  Libraries write banners to fd 1 (NCCL prints its version there
+    when NCCL_DEBUG is set on the box), so everything but the final line is sent to stderr."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 # ----------------------------------------------------------------------------------------- our arm
 def main():
     args = parse()
+    out = OneLineStdout()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import ctypes
 
@@ -365,7 +381,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, n_iter)
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
     lpd.finalize()
 
 
