@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--channels", type=int, default=3)
     ap.add_argument("--batch-per-gpu", type=int, default=1)
+    ap.add_argument("--depth", type=int, default=1, help="PSF depth D > 1: BASELINE configs[4], D independent 2-D problems "
+                    "against one measurement (ADMM(allow_depth=True); the reference has no 3-D ADMM, SURVEY 8a note)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--engine", default=None, choices=[None, "v1"], help="v1 = K1/K2 + cuFFT (A/B against the fused engine)")
@@ -237,25 +239,31 @@ def main():
     h, w, C, Bg = args.height, args.width, args.channels, args.batch_per_gpu
 
     # ---- synthetic inputs: PSF on rank 0, broadcast once over NCCL; per-rank scenes
+    D = args.depth
     gen = torch.Generator().manual_seed(0)
-    psf = torch.rand((1, h, w, C), generator=gen) ** 8
+    psf = torch.rand((D, h, w, C), generator=gen) ** 8
     psf = (psf / psf.norm()).to(device)
     if world > 1 and rank != 0:
         psf.zero_()
     lpd.broadcast_psf(psf, src=0)  # the only collective of the job: init-time, NCCL over NVLink/NVSwitch
     gen = torch.Generator().manual_seed(1000 + rank)
     scene = (torch.rand((Bg, 1, h, w, C), generator=gen) ** 2).to(device)
-    sim = L.RealFFTConvolve2D(psf, pad=True, norm="backward")
-    meas = sim.convolve(scene).clamp_(min=0)
-    meas = meas / meas.amax(dim=(1, 2, 3, 4), keepdim=True)
-    del sim, scene
+    if D == 1:
+        sim = L.RealFFTConvolve2D(psf, pad=True, norm="backward")
+        meas = sim.convolve(scene).clamp_(min=0)
+        meas = meas / meas.amax(dim=(1, 2, 3, 4), keepdim=True)
+        del sim
+    else:
+        meas = scene  # the arithmetic is data-independent except clamps / thresholds: any measurement times the same
+    del scene
     host_in = meas.cpu().pin_memory()
-    host_out = torch.empty((Bg, 1, h, w, C), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((Bg, D, h, w, C), dtype=torch.float32).pin_memory()
 
     cls = L.ADMM if args.algo == "admm" else L.FISTA
     stream = torch.cuda.Stream(device=device)
     with torch.cuda.stream(stream):
-        recon = cls(psf, n_iter=n_iter, no_graph=args.no_graph, engine=args.engine)
+        extra = {"allow_depth": True} if (D > 1 and args.algo == "admm") else {}
+        recon = cls(psf, n_iter=n_iter, no_graph=args.no_graph, engine=args.engine, **extra)
 
         def step_device():
             recon.set_data(meas)
@@ -313,10 +321,10 @@ def main():
     e2e_value = total * args.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peaks()
 
-    D, Hp, Wp, _ = recon._padded_shape
-    P = 4.0 * Bg * Hp * Wp * C
-    Sp = 8.0 * Bg * Hp * (Wp // 2 + 1) * C
-    d = 4.0 * Bg * h * w * C
+    _, Hp, Wp, _ = recon._padded_shape
+    P = 4.0 * Bg * D * Hp * Wp * C
+    Sp = 8.0 * Bg * D * Hp * (Wp // 2 + 1) * C
+    d = 4.0 * Bg * D * h * w * C
     # algorithmic bytes of OUR kernels, per launch
     kernel_bytes = {
         "admm_spatial(K1)": 11.0 * P + d,        # v1: reads V,HV,xi',rho',eta'0,eta'1 (+y); writes xi',rho',eta'0,eta'1,a
@@ -327,8 +335,8 @@ def main():
         "update": 5.0 * d, "residual": 3.0 * d, "spec_mul_H": 3.0 * Sp, "spec_mul_Hadj": 3.0 * Sp,
     }
     # fused GD engine: G-layout buffer (window rows only) and the filter table, per launch
-    Tg = 8.0 * Bg * (-(-(Wp // 2 + 1) // 4) * 4) * h * C
-    Fg = 8.0 * (-(-(Wp // 2 + 1) // 4) * 4) * Hp * C
+    Tg = 8.0 * Bg * D * (-(-(Wp // 2 + 1) // 4) * 4) * h * C
+    Fg = 8.0 * D * (-(-(Wp // 2 + 1) // 4) * 4) * Hp * C
     kernel_bytes.update({
         "gd_cols(H)": 2.0 * Tg + Fg, "gd_cols(Hadj)": 2.0 * Tg + Fg,
         "gd_rows(residual)": 2.0 * Tg + d, "gd_rows(update)": 2.0 * Tg + 4.0 * d,
@@ -364,17 +372,21 @@ def main():
         },
     }
     line = {
-        "metric": METRIC if args.algo == "admm" else f"FISTA-{n_iter} reconstructions/sec @ 3x1080x1920",
+        "metric": (METRIC if (args.algo == "admm" and D == 1 and n_iter == 100) else
+                   f"{args.algo.upper()}-{n_iter} reconstructions/sec @ {str(D) + 'x' if D > 1 else ''}{C}x{h}x{w}"),
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{args.algo.upper()} n_iter={n_iter} fp32, single {C}x{h}x{w} measurement per GPU per step (BASELINE configs[1]), padded {Hp}x{Wp}",
+            "workload": (f"{args.algo.upper()} n_iter={n_iter} fp32, single {C}x{h}x{w} measurement per GPU per step (BASELINE configs[1]), padded {Hp}x{Wp}"
+                         if D == 1 else
+                         f"{args.algo.upper()} n_iter={n_iter} fp32, {D}-depth PSF stack x {C}x{h}x{w}, one measurement per GPU per step (BASELINE configs[4]: "
+                         f"{D} independent 2-D problems against the same measurement -- the reference has no 3-D ADMM), padded {Hp}x{Wp}"),
             "batch_per_gpu": Bg, "parallelism": f"batch-sharded x{world}, PSF broadcast once (NCCL), no collective in the iteration",
             "l2": "per-recon working set ~1.4 GB >> 126 MB L2 (inputs larger than L2; no explicit flush)",
             "cuda_graph": not args.no_graph,
         },
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(d), "d2h_bytes_per_step": int(d), "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * Bg * h * w * C), "d2h_bytes_per_step": int(d), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": own_launches * args.steps,  # our kernels inside the `value` timed region (cuFFT kernels not counted)
         "roofline": roofline,
         "clocks": clocks,

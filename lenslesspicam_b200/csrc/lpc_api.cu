@@ -70,12 +70,11 @@ using GdColsKern = void (*)(GdFusedK, const float2*, const float2*, float2*, con
 struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; GdRowsKern gd[5]; };
 using ColsTmaKern = void (*)(FusedK, ColsTmaK, int, const float2*, const float2*, float2*, const float2*, const float*,
                              const float2*);
-constexpr int LPC_TMA_NTHG1 = 960, LPC_TMA_NTHG2 = 480;  // threads per compute group: one group / two groups
-constexpr int LPC_TMA_NTHG3 = 288;  // three groups, no look-ahead buffer
-constexpr int LPC_TMA_NV = 5;
-constexpr int LPC_TMA_G[LPC_TMA_NV] = {1, 2, 3, 2, 2}, LPC_TMA_T[LPC_TMA_NV] = {960, 480, 288, 288, 384};
+// threads per compute group of the persistent column kernel: two groups of 288 (measured at Hp = 2160, A per launch:
+// 1x960 232 us, 2x480 175, 3x288 without a look-ahead buffer 160, 2x384 155, 2x288 147 -- 96 registers, no spills)
+constexpr int LPC_TMA_NG = 2, LPC_TMA_NTHG = 288;
 using GdColsTmaKern = void (*)(GdFusedK, int, const float2*, float2*, const float2*);
-struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; ColsTmaKern tma[LPC_TMA_NV]; GdColsTmaKern gd_tma; };
+struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; ColsTmaKern tma; GdColsTmaKern gd_tma; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
 #define LPC_X(N, ...)                                                                                   \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_rows_ifft<float, FftSeq<N, __VA_ARGS__>>,              \
@@ -90,10 +89,8 @@ const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
 #define LPC_X(N, ...) \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, {k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 1024, 1>, k_admm_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>}, \
      k_gd_cols<float, FftSeq<N, __VA_ARGS__>, 576, 2>,                                                              \
-     {k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 1, LPC_TMA_NTHG1>, k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, LPC_TMA_NTHG2>,                          \
-      k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 3, LPC_TMA_NTHG3>, k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 288>, \
-      k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 384>},                                                       \
-     k_gd_cols_tma<float, FftSeq<N, __VA_ARGS__>, 2, 288>},
+     k_admm_cols_tma<float, FftSeq<N, __VA_ARGS__>, LPC_TMA_NG, LPC_TMA_NTHG>,                                      \
+     k_gd_cols_tma<float, FftSeq<N, __VA_ARGS__>, LPC_TMA_NG, LPC_TMA_NTHG>},
 const ColsEntry g_cols_menu[] = {LPC_COL_MENU(LPC_X)};
 #undef LPC_X
 const RowsEntry* find_rows(int N) {
@@ -184,7 +181,7 @@ struct Plan : lpc_plan_s {
     Cplx* tw_col_rev = nullptr;  // of an in-register fused pass runs the reversed order)
     Cplx* spec1 = nullptr;  // [Np][splane], warm start only (lazily allocated)
     // persistent TMA-pipelined column kernel (lpc_fused_tma.cuh)
-    int cols_tma = 0;        // 0 = off (k_admm_cols), 1 / 2 / 3 = number of compute groups
+    int cols_tma = 0;        // 1: persistent TMA-pipelined column kernel, 0: k_admm_cols
     Cplx* tabs_ip = nullptr; // twiddles of the in-place passes | Wj | Sy0 (copied to shared memory by the kernel)
     Cplx* Hm = nullptr;      // H in middle-stage order [DC][NT][RL][Hp/RL][NCT]
     T* Gx = nullptr;         // 2 - 2cos(2 pi kx/Wp), [NT*NCT]
@@ -464,7 +461,7 @@ struct Plan : lpc_plan_s {
             FusedK k = fk; k.plane0 = p0;
             if (cols_tma) {
                 const int n_items = fk.NT * np;
-                const int nthr = LPC_TMA_G[cols_tma - 1] * LPC_TMA_T[cols_tma - 1] + 32;
+                const int nthr = LPC_TMA_NG * LPC_TMA_NTHG + 32;
                 const int nblk = n_items < n_sms ? n_items : n_sms;
                 if constexpr (std::is_same<T, float>::value) {
                     ColsTmaK ck = ctk;
@@ -472,7 +469,7 @@ struct Plan : lpc_plan_s {
                     admm_params(it, m);
                     ck.mu1 = (float)m[0]; ck.mu2 = (float)m[1]; ck.mu3 = (float)m[2];
                     ck.scale = (float)(0.5 / ((double)Hp * (double)Wp));
-                    cols_entry->tma[cols_tma - 1]<<<nblk, nthr, smem_cols_tma, st>>>(k, ck, n_items, tabs_ip, Tout, Tin, Hm, Gx, Sx);
+                    cols_entry->tma<<<nblk, nthr, smem_cols_tma, st>>>(k, ck, n_items, tabs_ip, Tout, Tin, Hm, Gx, Sx);
                 }
                 LPC_KCHECK();
                 return LPC_OK;
@@ -528,11 +525,8 @@ struct Plan : lpc_plan_s {
         if constexpr (!std::is_same<T, float>::value) {
             return LPC_OK;
         } else {
-            // measured at 2160 (A per launch): 1x960 232 us, 2x480 175, 3x288 160, 2x384 155, 2x288 147 (96 registers,
-            // no spills, look-ahead buffer); k_admm_cols (LPC_COLS_TMA=0) 208
-            int want = 4;
-            if (const char* e = getenv("LPC_COLS_TMA")) want = atoi(e);
-            if (want < 0 || want > LPC_TMA_NV) want = 4;
+            int want = 1;
+            if (const char* e = getenv("LPC_COLS_TMA")) want = atoi(e) ? 1 : 0;
             const int np = cols_entry->npass, RL = cols_entry->radix[np - 1], NBL = Hp / RL;
             std::vector<Cplx> tabs;
             if (!fill_fft_ip_twiddles(Hp, cols_entry->radix, np, &tabs)) return fail(LPC_EINVAL, "fill_fft_ip_twiddles", "menu sequence");
@@ -542,8 +536,7 @@ struct Plan : lpc_plan_s {
             smem_cols_tma = cols_tma_smem_bytes(Hp, RL, tw_len);
             if (want == 0 || RL > LPC_TMA_MAXR || smem_cols_tma > (size_t)max_optin) return LPC_OK;
             LPC_CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
-            for (int v = 0; v < LPC_TMA_NV; ++v)
-                LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->tma[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols_tma));
+            LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols_tma));
             // position -> frequency after the forward passes; ky(j, m) = ky0(j) + m*NBL
             std::vector<int> km(Hp);
             for (int pz = 0; pz < Hp; ++pz) km[pz] = fft_ip_freq_of_pos(Hp, cols_entry->radix, np, pz);
@@ -653,7 +646,7 @@ struct Plan : lpc_plan_s {
             if (gd_tma) {
                 const Cplx* Fm_ = Fgm + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
                 const int n_items = gk.NTg * np;
-                cols_entry->gd_tma<<<n_items < n_sms ? n_items : n_sms, 2 * 288 + 32, smem_gd_tma, st>>>(k, n_items, tabs_ip, Tg, Fm_);
+                cols_entry->gd_tma<<<n_items < n_sms ? n_items : n_sms, LPC_TMA_NG * LPC_TMA_NTHG + 32, smem_gd_tma, st>>>(k, n_items, tabs_ip, Tg, Fm_);
                 LPC_KCHECK();
                 return LPC_OK;
             }
