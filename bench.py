@@ -199,6 +199,37 @@ def cpu_baseline(args, n_iter):
     }
 
 
+def torch_baseline_gpu(args, n_iter, device, psf, meas):
+    """The reference's TORCH path on the SAME GPU ('the real bar for the fused
+    kernels'): oracle/lensless_oracle_torch.py restates lensless/recon/{admm,gd}.py's torch branch operation for
+    operation (pinned against the reference's torch outputs in tests/); timed with explicit synchronisation on a
+    bounded sample and scaled to n_iter."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lensless_oracle_torch as ot
+
+    solver = ot.ALGOS[args.algo](psf)
+    solver.set_data(meas[:1])
+    solver.reset()
+    solver.update()
+    k = 5
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        solver.update()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / k
+    del solver
+    torch.cuda.empty_cache()
+    return {
+        "value": 1.0 / (ms * 1e-3 * n_iter), "unit": UNIT, "kind": "port (torch ops of the reference's torch branch, same GPU)",
+        "ms_per_iter": ms, "sample": f"{k} timed full-size iterations after 1 warm-up, CUDA events + synchronize, scaled x{n_iter}",
+    }
+
+
 # ----------------------------------------------------------------------------------------- stdout hygiene
 class OneLineStdout:
     """Rank 0 must print exactly ONE JSON line.  Libraries write banners to fd 1 (NCCL prints its version there
@@ -393,6 +424,11 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, n_iter)
+        if D == 1:
+            try:
+                line["torch_baseline_gpu"] = torch_baseline_gpu(args, n_iter, device, psf, meas)
+            except Exception as e:  # never lose the bench line to the extra baseline
+                line["torch_baseline_gpu"] = {"unavailable": repr(e)[:200]}
     out.emit(json.dumps(line))
     lpd.finalize()
 

@@ -797,7 +797,8 @@ struct Plan : lpc_plan_s {
     int set_psf(const void* dev_psf, cudaStream_t st) override {
         LPC_CK(cudaSetDevice(device));
         if (!dev_psf) return fail(LPC_EINVAL, "set_psf", "null PSF");
-        drop_graph();
+        // (the captured iteration graph stays valid: a new PSF rewrites the H / filter tables in place, no kernel
+        //  argument depends on it -- per-sample PSFs of a multi-mask evaluation loop, eval/benchmark.py:244-245)
         const T* psf = (const T*)dev_psf;
         int rc;
         // pad (rfft_convolve.py:84-100) -> rfft2 (rfft_convolve.py:121-123)

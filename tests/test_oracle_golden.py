@@ -132,3 +132,19 @@ def test_oracle_unrolled_matches_reference():
     out = orc.reconstruct("unrolled_fista", g["psf"].astype(np.float64), g["batch"][0].astype(np.float64), n, dtype="float64",
                           alpha=g["alpha"], tk=g["tk"])
     assert rel_to_max(out, g["unrolled_fista_t64"][0]) <= 1e-10
+
+
+def test_torch_restatement_matches_reference():
+    """oracle/lensless_oracle_torch.py (the reference's torch branch restated; timed on the GPU by bench.py as the
+    'reference torch path on the same device') against the reference's own torch-fp32 outputs."""
+    import torch
+
+    import lensless_oracle_torch as ot
+
+    for case in ("small_even_rgb", "small_odd_rgb", "small_gray"):
+        g = load_golden(case)
+        for algo, n in (("admm", 30), ("fista", 30)):
+            s = ot.ALGOS[algo](torch.from_numpy(g["psf"]))
+            s.set_data(torch.from_numpy(g["data"]))
+            out = s.apply(n).numpy()
+            assert rel_to_max(out, g[f"{algo}_t32_{n}"]) <= 2e-6, (case, algo)
