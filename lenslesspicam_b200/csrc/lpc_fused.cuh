@@ -68,28 +68,40 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
     using C = typename CxT<T>::type;
     constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
     CtaFftStatic<T, SEQ, -1, 1, NTH>::run(W, tw, tid);
-    for (int t = tid; t < NT; t += NTH) {
-        C a[NCT], x[NCT];
-#pragma unroll
-        for (int c = 0; c < NCT; ++c) {
-            const int kx = t * NCT + c;
-            a[c].x = a[c].y = x[c].x = x[c].y = T(0);
+    if constexpr (sizeof(T) == 4 && NCT == 2) {
+        // one COLUMN per lane: the 16-byte piece (A[kx], Xi[kx]) of the 32-byte chunk.  Two adjacent lanes fill a
+        // chunk (one sector), a warp instruction touches 16 lines instead of the 32 of a chunk-per-lane store
+        // (ncu: ~1.6 LSU wavefronts per lane for those), and the shared-memory reads are unit-stride.
+        for (int kx = tid; kx < NT * NCT; kx += NTH) {
+            Vec16<T> o;
+            o.v[0] = o.v[1] = o.v[2] = o.v[3] = T(0);
             if (kx < Nh) {
                 const C zk = W[fft_pad(kx, PADSH)];
                 const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PADSH)];
-                a[c].x = (zk.x + zm.x) * sep_scale;  // Z[k] + conj(Z[-k])
-                a[c].y = (zk.y - zm.y) * sep_scale;
-                x[c].x = (zk.y + zm.y) * sep_scale;  // (Z[k] - conj(Z[-k])) / i
-                x[c].y = (zm.x - zk.x) * sep_scale;
+                o.v[0] = (zk.x + zm.x) * sep_scale;  // A  = Z[k] + conj(Z[-k])
+                o.v[1] = (zk.y - zm.y) * sep_scale;
+                o.v[2] = (zk.y + zm.y) * sep_scale;  // Xi = (Z[k] - conj(Z[-k])) / i
+                o.v[3] = (zm.x - zk.x) * sep_scale;
             }
+            st16(reinterpret_cast<T*>(Tdst + (int64_t)(kx / NCT) * tile_stride + (int64_t)row * (2 * NCT) + (kx % NCT) * 2), o);
         }
-        C* dst = Tdst + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
-        if constexpr (sizeof(T) == 4 && NCT == 2) {
-            Vec32f o;  // one 32-byte store per chunk: (A[kx], Xi[kx], A[kx+1], Xi[kx+1])
-            o.v[0] = a[0].x; o.v[1] = a[0].y; o.v[2] = x[0].x; o.v[3] = x[0].y;
-            o.v[4] = a[1].x; o.v[5] = a[1].y; o.v[6] = x[1].x; o.v[7] = x[1].y;
-            st32(reinterpret_cast<float*>(dst), o);
-        } else {
+    } else {
+        for (int t = tid; t < NT; t += NTH) {
+            C a[NCT], x[NCT];
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) {
+                const int kx = t * NCT + c;
+                a[c].x = a[c].y = x[c].x = x[c].y = T(0);
+                if (kx < Nh) {
+                    const C zk = W[fft_pad(kx, PADSH)];
+                    const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PADSH)];
+                    a[c].x = (zk.x + zm.x) * sep_scale;  // Z[k] + conj(Z[-k])
+                    a[c].y = (zk.y - zm.y) * sep_scale;
+                    x[c].x = (zk.y + zm.y) * sep_scale;  // (Z[k] - conj(Z[-k])) / i
+                    x[c].y = (zm.x - zk.x) * sep_scale;
+                }
+            }
+            C* dst = Tdst + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
 #pragma unroll
             for (int c = 0; c < NCT; ++c) { dst[2 * c] = a[c]; dst[2 * c + 1] = x[c]; }
         }
@@ -117,35 +129,28 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     const int Hp = f.Hp;
     const int64_t tile_stride = (int64_t)Hp * (2 * NCT);
     const C* src0 = Tin + (int64_t)p * NT * tile_stride + (int64_t)row * (2 * NCT);
-    constexpr int IT = (NT + NTH - 1) / NTH;
-    // all 32-byte chunks of the row in flight at once
+    // one COLUMN per lane: the 16-byte piece (Vhat[kx], HVhat[kx]) of the 32-byte chunk (two adjacent lanes share a
+    // sector: 16 lines per warp instruction, unit-stride shared-memory stores); all pieces in flight at once
     static_assert(sizeof(T) == 4 && NCT == 2, "the fused engine is float-only with 32-byte chunks");
-    Vec32f ch[IT];
+    constexpr int NK = NT * NCT;
+    constexpr int IT = (NK + NTH - 1) / NTH;
+    Vec16<T> pc[IT];
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
-        const int t = tid + it * NTH;
-        if (t < NT) ch[it] = ld32_nc(reinterpret_cast<const float*>(src0 + (int64_t)t * tile_stride));
+        const int kx = tid + it * NTH;
+        if (kx < NK) pc[it] = ld16_nc(reinterpret_cast<const T*>(src0 + (int64_t)(kx / NCT) * tile_stride + (kx % NCT) * 2));
     }
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
-        const int t = tid + it * NTH;
-        if (t < NT) {
-            // chunk = (Vhat[kx], HVhat[kx], Vhat[kx+1], HVhat[kx+1])
-#pragma unroll
-            for (int c = 0; c < NCT; ++c) {
-                const int kx = t * NCT + c;
-                C vh, hh;
-                vh.x = ch[it].v[4 * c]; vh.y = ch[it].v[4 * c + 1];
-                hh.x = ch[it].v[4 * c + 2]; hh.y = ch[it].v[4 * c + 3];
-                if (kx < Nh) {
-                    C y; y.x = vh.x - hh.y; y.y = vh.y + hh.x;
-                    W[fft_pad(kx, PADSH)] = y;
-                    const int m = Wp - kx;
-                    if (kx >= 1 && m >= Nh) {
-                        C ym; ym.x = vh.x + hh.y; ym.y = hh.x - vh.y;
-                        W[fft_pad(m, PADSH)] = ym;
-                    }
-                }
+        const int kx = tid + it * NTH;
+        if (kx < Nh) {
+            const T vx = pc[it].v[0], vy = pc[it].v[1], hx = pc[it].v[2], hy = pc[it].v[3];
+            C y; y.x = vx - hy; y.y = vy + hx;
+            W[fft_pad(kx, PADSH)] = y;
+            const int m = Wp - kx;
+            if (kx >= 1 && m >= Nh) {
+                C ym; ym.x = vx + hy; ym.y = hx - vy;
+                W[fft_pad(m, PADSH)] = ym;
             }
         }
     }

@@ -82,28 +82,26 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
     C* Tp = Tg + (int64_t)p * NTg * tile_stride;
 
     if (MODE != LPC_GD_INIT) {
-        // gather the two half-spectrum rows, build the full-length packed row Y_a + i*Y_b
-        for (int t = tid; t < NTg; t += NTH) {
-            const C* sa = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC;
-            C ya[NC], yb[NC];
-            {
-                const Vec32f va = ld32_nc(reinterpret_cast<const float*>(sa));  // one 32-byte load per (tile,row) chunk
-                Vec32f vb;
+        // gather the two half-spectrum rows, build the full-length packed row Y_a + i*Y_b.  Two lanes per 32-byte
+        // chunk, each taking two columns (16 bytes) of row a and of row b: a warp instruction touches 16 lines
+        // instead of the 32 of a chunk-per-lane load (~1.6 LSU wavefronts per lane under ncu)
+        for (int g = tid; g < NTg * 2; g += NTH) {
+            const int t = g >> 1, hf = g & 1;
+            const C* sa = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC + hf * 2;
+            const Vec16<T> va = ld16_nc(reinterpret_cast<const T*>(sa));
+            Vec16<T> vb;
+            vb.v[0] = vb.v[1] = vb.v[2] = vb.v[3] = T(0);
+            if (has_b) vb = ld16_nc(reinterpret_cast<const T*>(sa + NC));
 #pragma unroll
-                for (int e = 0; e < 8; ++e) vb.v[e] = 0.f;
-                if (has_b) vb = ld32_nc(reinterpret_cast<const float*>(sa + NC));
-#pragma unroll
-                for (int c = 0; c < NC; ++c) { ya[c].x = va.v[2 * c]; ya[c].y = va.v[2 * c + 1]; yb[c].x = vb.v[2 * c]; yb[c].y = vb.v[2 * c + 1]; }
-            }
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const int kx = t * NC + c;
+            for (int c = 0; c < 2; ++c) {
+                const int kx = t * NC + hf * 2 + c;
+                const T yax = va.v[2 * c], yay = va.v[2 * c + 1], ybx = vb.v[2 * c], yby = vb.v[2 * c + 1];
                 if (kx < Nh) {
-                    C y; y.x = ya[c].x - yb[c].y; y.y = ya[c].y + yb[c].x;
+                    C y; y.x = yax - yby; y.y = yay + ybx;
                     W[fft_pad(kx, PI)] = y;
                     const int m = Wp - kx;
                     if (kx >= 1 && m >= Nh) {
-                        C ym; ym.x = ya[c].x + yb[c].y; ym.y = yb[c].x - ya[c].y;
+                        C ym; ym.x = yax + yby; ym.y = ybx - yay;
                         W[fft_pad(m, PI)] = ym;
                     }
                 }
@@ -180,26 +178,25 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
     __syncthreads();
     SeqTraits<REV>::template run_butfirst<T, -1, 1, NTH>(W, twF, tid);
 
-    // separate the packed pair and store the two half-spectrum rows (no 1/2: folded into the filter)
-    for (int t = tid; t < NTg; t += NTH) {
-        C a[NC], b[NC];
+    // separate the packed pair and store the two half-spectrum rows (no 1/2: folded into the filter); two lanes per
+    // 32-byte chunk, 16-byte stores (see the gather)
+    for (int g = tid; g < NTg * 2; g += NTH) {
+        const int t = g >> 1, hf = g & 1;
+        Vec16<T> oa, ob;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int kx = t * NC + c;
-            a[c].x = a[c].y = b[c].x = b[c].y = T(0);
+        for (int c = 0; c < 2; ++c) {
+            const int kx = t * NC + hf * 2 + c;
+            oa.v[2 * c] = oa.v[2 * c + 1] = ob.v[2 * c] = ob.v[2 * c + 1] = T(0);
             if (kx < Nh) {
                 const C zk = W[fft_pad(kx, PF)];
                 const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PF)];
-                a[c].x = zk.x + zm.x; a[c].y = zk.y - zm.y;   // Z[k] + conj(Z[-k])
-                b[c].x = zk.y + zm.y; b[c].y = zm.x - zk.x;   // (Z[k] - conj(Z[-k])) / i
+                oa.v[2 * c] = zk.x + zm.x; oa.v[2 * c + 1] = zk.y - zm.y;   // Z[k] + conj(Z[-k])
+                ob.v[2 * c] = zk.y + zm.y; ob.v[2 * c + 1] = zm.x - zk.x;   // (Z[k] - conj(Z[-k])) / i
             }
         }
-        C* da = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC;
-        Vec32f oa, ob;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { oa.v[2 * c] = a[c].x; oa.v[2 * c + 1] = a[c].y; ob.v[2 * c] = b[c].x; ob.v[2 * c + 1] = b[c].y; }
-        st32(reinterpret_cast<float*>(da), oa);
-        if (has_b) st32(reinterpret_cast<float*>(da + NC), ob);
+        C* da = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC + hf * 2;
+        st16(reinterpret_cast<T*>(da), oa);
+        if (has_b) st16(reinterpret_cast<T*>(da + NC), ob);
     }
 }
 
