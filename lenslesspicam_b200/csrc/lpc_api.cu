@@ -193,6 +193,8 @@ struct Plan : lpc_plan_s {
     FusedK fk{};
     size_t smem_row = 0, smem_col = 0;
     bool vh_valid = false;  // VH holds the V / HV of the current iterate
+    int dir_toggle = 0;     // direction of the next fused ADMM launch (FusedK::rev); alternates launch by launch
+    int dir_enable = 1;
     // engine v2 for the GD family (lpc_fused_gd.cuh)
     bool gd2 = false;
     Cplx* Tg = nullptr;     // G-layout spectral buffer [Np][NTg][h][4], updated in place
@@ -380,6 +382,7 @@ struct Plan : lpc_plan_s {
             if (want < 1) want = 1;
             n_chains = want;
             if (const char* e = getenv("LPC_PLANE_MAJOR")) plane_major = atoi(e) ? 1 : 0;
+            if (const char* e = getenv("LPC_ALTERNATE")) dir_enable = atoi(e) ? 1 : 0;
             if (const char* e = getenv("LPC_VH_SHARED")) vh_shared = atoi(e) ? 1 : 0;
             LPC_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
             for (int i = 1; i < n_chains; ++i) {
@@ -424,11 +427,12 @@ struct Plan : lpc_plan_s {
     int ry_log2 = 0;       // B2 processes 1 << ry_log2 rows per CTA (measured: 1 row 315 us, 2 rows 400, 4 rows 465)
     int cols_variant = 1;  // A: 0 = 1024 threads x 1 CTA/SM, 1 = 576 threads x 2 CTAs/SM
 
+    int next_dir() { const int d = dir_enable ? dir_toggle : 0; dir_toggle ^= 1; return d; }
     int launch_rows_ifft(cudaStream_t st, int p0 = 0, int np = -1, T* vh = nullptr) {
         if constexpr (std::is_same<T, float>::value) {
             if (np < 0) np = Np;
             dim3 grid(Hp, np);
-            FusedK k = fk; k.plane0 = p0;
+            FusedK k = fk; k.plane0 = p0; k.rev = next_dir();
             rows_entry->ifft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, Tin, vh ? vh : VH);
             LPC_KCHECK();
         }
@@ -447,7 +451,7 @@ struct Plan : lpc_plan_s {
             if (np < 0) np = Np;
             const int ry = 1 << ry_log2;
             dim3 grid((Hp + ry - 1) / ry, np);
-            FusedK k = fk; k.plane0 = p0;
+            FusedK k = fk; k.plane0 = p0; k.rev = next_dir();
             rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, admm_k(it, true), tw_row, vh ? vh : VH, Tout, data,
                                                                           AX + (int64_t)Np * plane, rho, eta_i, eta_o);
             LPC_KCHECK();
@@ -458,7 +462,7 @@ struct Plan : lpc_plan_s {
         if constexpr (std::is_same<T, float>::value) {
             if (np < 0) np = Np;
             dim3 grid(fk.NT, np);
-            FusedK k = fk; k.plane0 = p0;
+            FusedK k = fk; k.plane0 = p0; k.rev = cols_tma ? next_dir() : 0;
             if (cols_tma) {
                 const int n_items = fk.NT * np;
                 const int nthr = LPC_TMA_NG * LPC_TMA_NTHG + 32;

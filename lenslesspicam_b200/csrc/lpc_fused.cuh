@@ -55,7 +55,12 @@ struct FusedK {
     int Hp, Wp, Nh, NT;  // NT tiles of LPC_NCT columns cover Nh = Wp/2+1
     int n_planes, DC;
     int plane0;  // first plane of this launch (the planes of a plan are split over concurrent streams)
+    int rev;     // 1: walk rows / tiles and planes in DESCENDING order.  Consecutive launches alternate, so a kernel
+                 // starts on what its predecessor wrote last -- the part of the hand-off still in the 126 MB L2
 };
+// logical (row or tile, plane) of a CTA under the launch's direction
+__device__ __forceinline__ int lpc_dir_x(const FusedK& f, int n) { return f.rev ? n - 1 - (int)blockIdx.x : (int)blockIdx.x; }
+__device__ __forceinline__ int lpc_dir_y(const FusedK& f) { return f.plane0 + (f.rev ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y); }
 
 constexpr int LPC_ROWS_RY = 4;  // rows a B2 CTA processes back to back
 
@@ -83,7 +88,8 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
                 o.v[2] = (zk.y + zm.y) * sep_scale;  // Xi = (Z[k] - conj(Z[-k])) / i
                 o.v[3] = (zm.x - zk.x) * sep_scale;
             }
-            st16(reinterpret_cast<T*>(Tdst + (int64_t)(kx / NCT) * tile_stride + (int64_t)row * (2 * NCT) + (kx % NCT) * 2), o);
+            st16_hint(reinterpret_cast<T*>(Tdst + (int64_t)(kx / NCT) * tile_stride + (int64_t)row * (2 * NCT) + (kx % NCT) * 2), o,
+                      LPC_L2_EVICT_LAST);  // the column kernel reads it next
         }
     } else {
         for (int t = tid; t < NT; t += NTH) {
@@ -125,8 +131,8 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* W = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int row = blockIdx.x, p = f.plane0 + blockIdx.y;
     const int Hp = f.Hp;
+    const int row = lpc_dir_x(f, Hp), p = lpc_dir_y(f);
     const int64_t tile_stride = (int64_t)Hp * (2 * NCT);
     const C* src0 = Tin + (int64_t)p * NT * tile_stride + (int64_t)row * (2 * NCT);
     // one COLUMN per lane: the 16-byte piece (Vhat[kx], HVhat[kx]) of the 32-byte chunk (two adjacent lanes share a
@@ -138,7 +144,8 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
         const int kx = tid + it * NTH;
-        if (kx < NK) pc[it] = ld16_nc(reinterpret_cast<const T*>(src0 + (int64_t)(kx / NCT) * tile_stride + (kx % NCT) * 2));
+        if (kx < NK) pc[it] = ld16_nc_hint(reinterpret_cast<const T*>(src0 + (int64_t)(kx / NCT) * tile_stride + (kx % NCT) * 2),
+                                           LPC_L2_EVICT_FIRST);  // last use of Tin
     }
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
@@ -169,9 +176,9 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
         fft_bfly_load<T, RL>(W, 0, 1, PADSH, Wp, j, v);
         fft_bfly_compute<T, RL, +1>(v, tw + TR::tw_off_last, NSL, j);
 #pragma unroll
-        for (int m = 0; m < RL; ++m) {
-            Vout[j + m * NSL] = v[m].x;
-            HVout[j + m * NSL] = v[m].y;
+        for (int m = 0; m < RL; ++m) {  // B2 reads them next
+            st4_hint(Vout + j + m * NSL, v[m].x, LPC_L2_EVICT_LAST);
+            st4_hint(HVout + j + m * NSL, v[m].y, LPC_L2_EVICT_LAST);
         }
     }
 }
@@ -215,7 +222,7 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* W = reinterpret_cast<C*>(smem_raw);
     const int tid = threadIdx.x;
-    const int p = f.plane0 + blockIdx.y;
+    const int p = lpc_dir_y(f);
     const int Hp = f.Hp;
     const int64_t plane = (int64_t)Hp * Wp;
     const int64_t base = (int64_t)p * plane;
@@ -232,7 +239,7 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
     const int64_t tile_stride = (int64_t)Hp * (2 * NCT);
     C* ToutP = Tout + (int64_t)p * NT * tile_stride;
 
-    const int i0 = blockIdx.x * RY;
+    const int i0 = lpc_dir_x(f, (Hp + RY - 1) / RY) * RY;
     for (int r = 0; r < RY; ++r) {
         const int i = i0 + r;
         if (i >= Hp) break;
@@ -250,16 +257,20 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                     const int j = 4 * q;
                     const int jr = (j + 4 == Wp) ? 0 : j + 4;
                     const int jl = (j == 0) ? Wp - 1 : j - 1;
-                    const Vec16<T> vc = ld16_nc(V + ro + j), vp = ld16_nc(V + ru + j), vn = ld16_nc(V + rd + j);
-                    const Vec16<T> hv = ld16_nc(HV + ro + j);
-                    const Vec16<T> e0 = ld16_nc(eta0 + ro + j), e0d = ld16_nc(eta0 + rd + j), e1 = ld16_nc(eta1 + ro + j);
-                    const Vec16<T> xih = ld16(xip + ro + j), rhoh = ld16(rhop + ro + j);
+                    // the CTA that walks LAST over a row of V / eta'0 (row i-1's successor in the sweep direction) frees it
+                    const unsigned long long pol_up = f.rev ? LPC_L2_EVICT_NORMAL : LPC_L2_HALO;
+                    const unsigned long long pol_dn = f.rev ? LPC_L2_HALO : LPC_L2_EVICT_NORMAL;
+                    const Vec16<T> vc = ld16_nc(V + ro + j), vp = ld16_nc_hint(V + ru + j, pol_up), vn = ld16_nc_hint(V + rd + j, pol_dn);
+                    const Vec16<T> hv = ld16_nc_hint(HV + ro + j, LPC_L2_EVICT_FIRST);
+                    const Vec16<T> e0 = ld16_nc_hint(eta0 + ro + j, pol_up), e0d = ld16_nc_hint(eta0 + rd + j, pol_dn);
+                    const Vec16<T> e1 = ld16_nc_hint(eta1 + ro + j, LPC_L2_STREAM);
+                    const Vec16<T> xih = ld16_hint(xip + ro + j, LPC_L2_STREAM), rhoh = ld16_hint(rhop + ro + j, LPC_L2_STREAM);
                     const T e1r = __ldg(eta1 + ro + jr);
                     const T vl = __ldg(V + ro + jl), vr = __ldg(V + ro + jr);
                     Vec16<T> y;
                     y.v[0] = y.v[1] = y.v[2] = y.v[3] = T(0);
                     if (row_in && j >= k.dcol0 && j < k.dcol0 + k.dpitch)
-                        y = ld16_nc(dp + (int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0));
+                        y = ld16_nc_hint(dp + (int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0), LPC_L2_STREAM);
                     Vec16<T> t1, e1new, e0new, xin, rhon;
                     T t0[4], t0d[4], dummy, av[4];
 #pragma unroll
@@ -288,10 +299,10 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
 #pragma unroll
                         for (int e = 0; e < 4; ++e) { C z; z.x = av[e]; z.y = xin.v[e]; W[fft_pad(j + e, PADSH)] = z; }
                     }
-                    st16(xip + ro + j, xin);
-                    st16(rhop + ro + j, rhon);
-                    st16(eta0_o + ro + j, e0new);
-                    st16(eta1_o + ro + j, e1new);
+                    st16_hint(xip + ro + j, xin, LPC_L2_STREAM);  // the duals are not touched again for a whole iteration
+                    st16_hint(rhop + ro + j, rhon, LPC_L2_STREAM);
+                    st16_hint(eta0_o + ro + j, e0new, LPC_L2_STREAM);
+                    st16_hint(eta1_o + ro + j, e1new, LPC_L2_STREAM);
                 }
             }
         } else {

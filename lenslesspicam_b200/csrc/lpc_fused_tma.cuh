@@ -65,6 +65,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
 }
+// the same two with an L2 eviction-priority policy (lpc_util.cuh)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* dst, uint32_t src_smem, uint32_t bytes, unsigned long long pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes),
+                 "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -138,11 +149,12 @@ k_admm_cols_tma(FusedK f, ColsTmaK ck, int n_items, const typename CxT<T>::type*
         // ------------------------------------------------------------------ producer warp (one lane)
         if (tid != NG * NTHG) return;
         auto issue_load = [&](int e) {
-            const int item = (int)blockIdx.x + e * (int)gridDim.x;
+            const int lin = (int)blockIdx.x + e * (int)gridDim.x, item = f.rev ? n_items - 1 - lin : lin;
             const int p = f.plane0 + item / NT, tile = item % NT, q = p % f.DC;
             const int b = e % NBUF;
             mbar_arrive_expect_tx(full_bar(b), TILE_BYTES);
-            bulk_g2s(smem_u32(bufs + (size_t)b * n), Tsrc + ((int64_t)p * NT + tile) * n, TILE_BYTES, full_bar(b));
+            bulk_g2s_hint(smem_u32(bufs + (size_t)b * n), Tsrc + ((int64_t)p * NT + tile) * n, TILE_BYTES, full_bar(b),
+                          LPC_L2_EVICT_FIRST);  // last use of Tout
             // H of the tile is read by the compute group about a tile time later: pull it into L2 now
             bulk_prefetch_l2(Hm + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT, (uint32_t)(Hp * NCT * sizeof(C)));
         };
@@ -150,9 +162,9 @@ k_admm_cols_tma(FusedK f, ColsTmaK ck, int n_items, const typename CxT<T>::type*
         for (int e = 0; e < count; ++e) {
             const int b = e % NBUF;
             mbar_wait(done_bar(b), (uint32_t)((e / NBUF) & 1));
-            const int item = (int)blockIdx.x + e * (int)gridDim.x;
+            const int lin = (int)blockIdx.x + e * (int)gridDim.x, item = f.rev ? n_items - 1 - lin : lin;
             const int p = f.plane0 + item / NT, tile = item % NT;
-            bulk_s2g(Tdst + ((int64_t)p * NT + tile) * n, smem_u32(bufs + (size_t)b * n), TILE_BYTES);
+            bulk_s2g_hint(Tdst + ((int64_t)p * NT + tile) * n, smem_u32(bufs + (size_t)b * n), TILE_BYTES, LPC_L2_EVICT_LAST);  // B1 reads it next
             bulk_commit();
             if (e + NBUF < count) {
                 bulk_wait_read0();  // the store has read the buffer: it may be overwritten
@@ -170,7 +182,7 @@ k_admm_cols_tma(FusedK f, ColsTmaK ck, int n_items, const typename CxT<T>::type*
     for (int e = grp; e < count; e += NG) {
         const int b = e % NBUF;
         C* sm = bufs + (size_t)b * n;
-        const int item = (int)blockIdx.x + e * (int)gridDim.x;
+        const int lin = (int)blockIdx.x + e * (int)gridDim.x, item = f.rev ? n_items - 1 - lin : lin;
         const int p = f.plane0 + item / NT, tile = item % NT, q = p % f.DC;
         const C* Hq = Hm + ((int64_t)q * NT + tile) * (int64_t)Hp * NCT;
         mbar_wait(full_bar(b), (uint32_t)((e / NBUF) & 1));
@@ -186,7 +198,7 @@ k_admm_cols_tma(FusedK f, ColsTmaK ck, int n_items, const typename CxT<T>::type*
         if (g < NPAIR) {
             const int c = g % NCT, j = g / NCT;
 #pragma unroll
-            for (int m = 0; m < RL; ++m) Hh[m] = __ldg(Hq + (m * NBL + j) * NCT + c);
+            for (int m = 0; m < RL; ++m) Hh[m] = ld8_nc_hint(Hq + (m * NBL + j) * NCT + c, LPC_L2_EVICT_FIRST);
             const int kx = tile * NCT + c, kxc = kx < f.Nh ? kx : 0;
             sxv = __ldg(Sx + kxc);
             gxv = __ldg(Gx + kxc);
@@ -228,7 +240,7 @@ k_admm_cols_tma(FusedK f, ColsTmaK ck, int n_items, const typename CxT<T>::type*
             if (gn < NPAIR) {
                 const int cn = gn % NCT, jn = gn / NCT;
 #pragma unroll
-                for (int m = 0; m < RL; ++m) Hh[m] = __ldg(Hq + (m * NBL + jn) * NCT + cn);
+                for (int m = 0; m < RL; ++m) Hh[m] = ld8_nc_hint(Hq + (m * NBL + jn) * NCT + cn, LPC_L2_EVICT_FIRST);
                 if (NTHG % NCT != 0) {  // the column changes only when the stride is odd
                     const int kx = tile * NCT + cn, kxc = kx < f.Nh ? kx : 0;
                     sxv = __ldg(Sx + kxc);

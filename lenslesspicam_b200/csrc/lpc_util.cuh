@@ -48,6 +48,52 @@ __device__ __forceinline__ void st32(float* p, const Vec32f& x) {
                  : "memory");
 }
 
+// ---- L2 eviction-priority hints (sm_80+ `.L2::cache_hint` with a 64-bit policy; the constants are the fixed
+// fractional-1.0 policies CUTLASS ships as TMA::CacheHintSm90).  The 126 MB L2 holds about half of one 199 MB
+// kernel-to-kernel hand-off of the fused ADMM engine, and consecutive launches walk in opposite directions
+// (FusedK::rev) so a consumer starts on what its producer wrote last.  MEASURED at 3x1080x1920 (recon/s, one run
+// each): no hints 20.65; bit 0 (hand-off writes evict-last) 20.76; + bit 1 (last-use reads of hand-offs
+// evict-first) 20.55; + bit 2 (duals / measurement evict-first) 20.51; + bit 3 (evict-first on the last sweep over
+// a halo row of V / eta') 19.84 -- CTAs run out of order, so "last" readers evict rows their neighbours still
+// need.  Default: bit 0 only.
+#ifndef LPC_L2_HINTS
+#define LPC_L2_HINTS 1
+#endif
+constexpr unsigned long long LPC_L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr unsigned long long LPC_L2_EF_ = 0x12F0000000000000ull, LPC_L2_EL_ = 0x14F0000000000000ull;
+constexpr unsigned long long LPC_L2_EVICT_LAST = (LPC_L2_HINTS & 1) ? LPC_L2_EL_ : LPC_L2_EVICT_NORMAL;   // hand-off writes
+constexpr unsigned long long LPC_L2_EVICT_FIRST = (LPC_L2_HINTS & 2) ? LPC_L2_EF_ : LPC_L2_EVICT_NORMAL;  // last-use reads of hand-offs
+constexpr unsigned long long LPC_L2_STREAM = (LPC_L2_HINTS & 4) ? LPC_L2_EF_ : LPC_L2_EVICT_NORMAL;       // duals, measurement
+constexpr unsigned long long LPC_L2_HALO = (LPC_L2_HINTS & 8) ? LPC_L2_EF_ : LPC_L2_EVICT_NORMAL;         // last sweep over a halo row
+__device__ __forceinline__ Vec16<float> ld16_nc_hint(const float* p, unsigned long long pol) {
+    Vec16<float> o;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(o.v[0]), "=f"(o.v[1]), "=f"(o.v[2]), "=f"(o.v[3])
+                 : "l"(p), "l"(pol));
+    return o;
+}
+__device__ __forceinline__ Vec16<float> ld16_hint(const float* p, unsigned long long pol) {
+    Vec16<float> o;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(o.v[0]), "=f"(o.v[1]), "=f"(o.v[2]), "=f"(o.v[3])
+                 : "l"(p), "l"(pol)
+                 : "memory");
+    return o;
+}
+__device__ __forceinline__ void st16_hint(float* p, const Vec16<float>& x, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]),
+                 "f"(x.v[3]), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st4_hint(float* p, float x, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(x), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float2 ld8_nc_hint(const float2* p, unsigned long long pol) {
+    float2 o;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(o.x), "=f"(o.y) : "l"(p), "l"(pol));
+    return o;
+}
+
 template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
 template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
 
