@@ -374,6 +374,33 @@ def test_full_size_admm_against_oracle_and_properties():
     assert rel_to_max(both[0].cpu().numpy(), full.cpu().numpy()) <= 1e-6  # batch == single
 
 
+def test_full_size_fista_against_oracle_and_properties():
+    """3x1080x1920, BASELINE configs[2]: three FISTA iterations against the CPU oracle in fp32 and fp64, then
+    size-independent properties at 12 iterations (channel independence, continuation == one run, gradient-descent
+    monotonicity of the data-fidelity term)."""
+    psf, data = orc.synthetic_problem(1080, 1920, 3, seed=1)
+    res, rec = run("fista", psf, data, 3)
+    out = res.cpu().numpy()
+    ref32 = orc.reconstruct("fista", psf, data, 3, workers=8)
+    ref64 = orc.reconstruct("fista", psf.astype(np.float64), data.astype(np.float64), 3, dtype="float64", workers=8)
+    e_ours, e_ref = rel_to_max(out, ref64), rel_to_max(ref32, ref64)
+    print(f"full size FISTA-3: ours vs fp64 {e_ours:.2e}; reference fp32 vs fp64 {e_ref:.2e}; ours vs fp32 {rel_to_max(out, ref32):.2e}")
+    assert e_ours <= TOL
+    assert rel_to_max(out, ref32) <= max(TOL, e_ref + e_ours + 1e-7)
+    full = rec.apply(n_iter=12, disp_iter=None)
+    gray, _ = run("fista", psf[..., 2:3], data[..., 2:3], 12)
+    # a gray PSF has its own step size alpha (max over ITS spectrum), like the channel of an RGB one: same numbers
+    assert rel_to_max(gray.cpu().numpy(), full[..., 2:3].cpu().numpy()) <= 1e-6
+    rec.apply(n_iter=5, disp_iter=None)
+    cont = rec.apply(n_iter=7, disp_iter=None, reset=False)
+    assert rel_to_max(cont.cpu().numpy(), full.cpu().numpy()) <= 1e-6  # 5 + 7 iterations == 12
+    errs = []
+    for n in (1, 4, 12):  # plain gradient descent with step < 2/L decreases the reconstruction error monotonically
+        g, grec = run("gd", psf, data, n)
+        errs.append(float(grec.reconstruction_error(prediction=g[None], normalize=False).cpu()))
+    assert errs[0] > errs[1] > errs[2], errs
+
+
 # ------------------------------------------------------------------------------ unrolled solvers (SURVEY 8f.1)
 def test_unrolled_admm_forward_matches_reference():
     """UnrolledADMM.forward(batch) with a DIFFERENT (mu1, mu2, mu3, tau) per iteration against the reference's
