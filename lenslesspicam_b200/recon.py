@@ -359,10 +359,31 @@ class ReconstructionAlgorithm(abc.ABC):
     def forward(self, batch, psfs=None, background=None):
         """Batched inference in the shape of ``TrainableReconstructionAlgorithm.forward``
         (trainable_recon.py:297-405, no learnable parameters): ``[B, D|1, h, w, C] -> [B, D, h, w, C]``."""
+        return self._forward_batch(batch, psfs, background)
+
+    def _forward_batch(self, batch, psfs, background, **apply_kw):
+        """``psfs``: None, one PSF ``[D, h, w, C]`` / ``[1, D, h, w, C]``, or one per sample ``[B, D, h, w, C]``
+        (multi-mask datasets, eval/benchmark.py:186-190,255-259).  A plan holds ONE transfer function per
+        (depth, channel), so per-sample PSFs run sample by sample -- ``_set_psf`` costs ~1 ms against a ~50 ms
+        reconstruction (scripts_dev/time_setpsf.py)."""
+        assert isinstance(batch, torch.Tensor) and len(batch.shape) == 5, "batch must be of shape (N, D, H, W, C)"
+        apply_kw.setdefault("disp_iter", None)
+        apply_kw.setdefault("plot", False)
+        B = int(batch.shape[0])
+        if psfs is not None and psfs.dim() == 5 and int(psfs.shape[0]) > 1:
+            assert int(psfs.shape[0]) == B, "one PSF per sample"
+            outs = []
+            for b in range(B):
+                self._set_psf(psfs[b])
+                self.set_data(batch[b : b + 1])
+                bg = background[b : b + 1] if (background is not None and background.dim() == 5) else background
+                o = self.apply(background=bg, **apply_kw)
+                outs.append(o[None] if self._B == 1 else o)
+            return torch.cat(outs, dim=0)
         if psfs is not None:
-            self._set_psf(psfs)
+            self._set_psf(psfs[0] if psfs.dim() == 5 else psfs)
         self.set_data(batch)
-        out = self.apply(disp_iter=None, plot=False, background=background)
+        out = self.apply(background=background, **apply_kw)
         return out[None] if self._B == 1 else out
 
     # ------------------------------------------------------------------ metrics

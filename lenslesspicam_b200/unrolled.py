@@ -72,10 +72,7 @@ class _UnrolledMixin:
         batch = self._prepare_batch(batch, background)
         if psfs is not None:
             assert psfs.shape[-3:] == batch.shape[-3:], "psfs must have the same shape as batch"
-            self._set_psf(psfs if psfs.dim() == 4 else psfs[0])
-        self.set_data(batch)
-        out = self.apply(n_iter=self._n_iter, disp_iter=None, plot=False)
-        return out[None] if self._B == 1 else out
+        return self._forward_batch(batch, psfs, None, n_iter=self._n_iter)
 
     batch_call = forward  # trainable_recon.py: alias kept for callers
 

@@ -458,3 +458,20 @@ def test_unrolled_rejects_processors_and_long_runs():
 
     with pytest.raises(LpcError):
         rec.apply(n_iter=4, disp_iter=None, plot=False)  # more iterations than schedule entries
+
+
+def test_forward_with_per_sample_psfs_matches_individual_runs():
+    """eval/benchmark.py:186-190,255-259: a multi-mask dataset hands ``forward`` one PSF per sample."""
+    g = load_golden("batch")
+    batch = dev(g["batch"])  # [4,1,24,32,3]
+    rng = np.random.default_rng(5)
+    psfs = np.stack([g["psf"] * (0.5 + rng.random(g["psf"].shape)).astype(np.float32) for _ in range(4)])
+    rec = L().ADMM(dev(g["psf"]), n_iter=10)
+    out = rec.forward(batch=batch, psfs=dev(psfs))
+    assert tuple(out.shape) == (4, 1, 24, 32, 3)
+    for b in range(4):
+        one, _ = run("admm", psfs[b], g["batch"][b], 10)
+        assert rel_to_max(out[b].cpu().numpy(), one.cpu().numpy()) <= 1e-6, b
+    # one shared PSF given as [1, D, h, w, C] is the batched path
+    out1 = rec.forward(batch=batch, psfs=dev(g["psf"])[None])
+    assert rel_to_max(out1.cpu().numpy(), g["admm_t32_10"]) <= TOL
