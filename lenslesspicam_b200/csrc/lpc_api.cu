@@ -496,7 +496,9 @@ struct Plan : lpc_plan_s {
             if (!rows_entry || !cols_entry) return LPC_OK;
             if (!make_fft_plan_from(Wp, rows_entry->radix, rows_entry->npass, &plan_row)) return LPC_OK;
             if (!make_fft_plan_from(Hp, cols_entry->radix, cols_entry->npass, &plan_col)) return LPC_OK;
-            smem_row = padded_bytes(Wp);
+            // exact size when the sequence needs no padding (odd first radix): 4 x (30 KB + 1 KB) fit the 132 KB
+            // carve-out step and leave 96 KB of L1 to the twiddle tables and the +-1 rows of V, instead of 64 KB
+            smem_row = (plan_row.padsh >= 30) ? (size_t)Wp * sizeof(Cplx) : padded_bytes(Wp);
             smem_col = padded_bytes(2 * LPC_NCT * Hp);
             int max_optin = 0;
             LPC_CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
