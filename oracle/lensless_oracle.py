@@ -2,8 +2,9 @@
 CPU oracle for the LenslessPiCam iterative-deconvolution hot path.
 
 THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
-``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
-legs of ``bench.py`` may import it.  The product path
+``__graft_entry__.smoke()`` and the baseline legs of ``bench.py``
+(``cpu_baseline``, ``--impl reference``, and ``torch_baseline_gpu``, which times
+the sibling ``lensless_oracle_torch.py``) may import it.  The product path
 (``lenslesspicam_b200``) never imports, links or executes anything here.
 
 It restates, in plain numpy + ``scipy.fft`` (pocketfft -- the same FFT the
