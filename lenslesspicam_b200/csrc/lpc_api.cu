@@ -195,6 +195,8 @@ struct Plan : lpc_plan_s {
     bool vh_valid = false;  // VH holds the V / HV of the current iterate
     int dir_toggle = 0;     // direction of the next fused ADMM launch (FusedK::rev); alternates launch by launch
     int dir_enable = 1;
+    int b2_prefetch = 256;  // B2: L2-prefetch distance in rows (0 = off).  Measured B2 per launch: off 224 us, 74 rows 223,
+                            // 148: 217, 222: 213, 296: 214, 400: 218, 592: 240, 1184: 255 (LPC_B2_PF)
     // engine v2 for the GD family (lpc_fused_gd.cuh)
     bool gd2 = false;
     Cplx* Tg = nullptr;     // G-layout spectral buffer [Np][NTg][h][4], updated in place
@@ -383,6 +385,7 @@ struct Plan : lpc_plan_s {
             n_chains = want;
             if (const char* e = getenv("LPC_PLANE_MAJOR")) plane_major = atoi(e) ? 1 : 0;
             if (const char* e = getenv("LPC_ALTERNATE")) dir_enable = atoi(e) ? 1 : 0;
+            if (const char* e = getenv("LPC_B2_PF")) b2_prefetch = atoi(e);
             if (const char* e = getenv("LPC_VH_SHARED")) vh_shared = atoi(e) ? 1 : 0;
             LPC_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
             for (int i = 1; i < n_chains; ++i) {
@@ -451,7 +454,7 @@ struct Plan : lpc_plan_s {
             if (np < 0) np = Np;
             const int ry = 1 << ry_log2;
             dim3 grid((Hp + ry - 1) / ry, np);
-            FusedK k = fk; k.plane0 = p0; k.rev = next_dir();
+            FusedK k = fk; k.plane0 = p0; k.rev = next_dir(); k.pf = b2_prefetch;
             rows_entry->spatial[ry_log2]<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, admm_k(it, true), tw_row, vh ? vh : VH, Tout, data,
                                                                           AX + (int64_t)Np * plane, rho, eta_i, eta_o);
             LPC_KCHECK();
