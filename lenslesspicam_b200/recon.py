@@ -432,6 +432,63 @@ class ReconstructionAlgorithm(abc.ABC):
         self._data_sent = False
         return host_out
 
+    def apply_host_stream(self, host_inputs, host_outputs, n_iter=None):
+        """Reconstruct a STREAM of host-resident measurements: ``host_inputs[k]`` (pinned ``[B, Dd, h, w, C]``) ->
+        ``host_outputs[k]`` (pinned ``[B, D, h, w, C]``).  Every measurement still pays its own H2D copy, reset,
+        ``n_iter`` iterations, crop/clamp and D2H copy, but the copies run on two side streams against double-buffered
+        device staging, so the copy of measurement k+1 and the read-back of k-1 overlap the iterations of k.
+        Returns after the last image has landed in host memory."""
+        assert len(host_inputs) == len(host_outputs) and len(host_inputs) > 0
+        if n_iter is None:
+            n_iter = self._n_iter
+        first = host_inputs[0]
+        assert first.dim() == 5 and not first.is_cuda and first.dtype == self._dtype
+        B, Dd = int(first.shape[0]), int(first.shape[1])
+        D, h, w, C = (int(v) for v in self._psf.shape)
+        plan = self._select_plan(B)
+        lib = _lib.load()
+        dev = self._device
+        if getattr(self, "_hs", None) is None or self._hs["key"] != (B, Dd):
+            self._hs = {
+                "key": (B, Dd),
+                "h2d": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev),
+                "din": [torch.empty((B, Dd, h, w, C), dtype=self._dtype, device=dev) for _ in range(2)],
+                "dout": [torch.empty((B, D, h, w, C), dtype=self._dtype, device=dev) for _ in range(2)],
+            }
+        hs = self._hs
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+        out_ready = [torch.cuda.Event() for _ in range(2)]
+        out_free = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        for ev in in_free + out_free:
+            ev.record(cur)
+        hs["h2d"].wait_stream(cur)
+        hs["d2h"].wait_stream(cur)
+        for k, (hin, hout) in enumerate(zip(host_inputs, host_outputs)):
+            s = k & 1
+            with torch.cuda.stream(hs["h2d"]):
+                hs["h2d"].wait_event(in_free[s])
+                hs["din"][s].copy_(hin, non_blocking=True)
+                in_ready[s].record(hs["h2d"])
+            cur.wait_event(in_ready[s])
+            with self._stream as st:
+                _lib.check(lib.lpc_set_data(plan, hs["din"][s].data_ptr(), Dd, None, None, None, None, st), plan)
+            in_free[s].record(cur)
+            cur.wait_event(out_free[s])
+            with self._stream as st:
+                _lib.check(lib.lpc_reset(plan, None, st), plan)
+                _lib.check(lib.lpc_run(plan, int(n_iter), st), plan)
+                _lib.check(lib.lpc_get_image(plan, hs["dout"][s].data_ptr(), st), plan)
+            out_ready[s].record(cur)
+            with torch.cuda.stream(hs["d2h"]):
+                hs["d2h"].wait_event(out_ready[s])
+                hout.copy_(hs["dout"][s], non_blocking=True)
+                out_free[s].record(hs["d2h"])
+        hs["d2h"].synchronize()
+        self._data_sent = False
+        return host_outputs
+
     def bytes_per_iter(self):
         """Algorithmic HBM bytes one iteration moves for the current batch."""
         lib = _lib.load()
