@@ -2,16 +2,17 @@
 GPU mirror of ``lensless.ADMM`` (reference: lensless/recon/admm.py:24-338):
 ADMM with an anisotropic-TV prior and a non-negativity constraint.
 
-Per iteration the engine runs two hand-written kernels and four cuFFT
-transforms (the reference: ~360 torch op dispatches and six FFTs):
+Per iteration the fused engine (default, fp32, padded sizes in the compiled menu) runs THREE hand-written
+kernels that own their FFTs (the reference: ~360 torch op dispatches and six FFTs):
 
-    K1  fused spatial pass  -- dual completion, U/X/W proxes, new half-duals,
-                               FFT operand a            (admm.py:232-263, 277-279, 298-311)
-    R2C(a), R2C(xi')
-    K2  spectral pass       -- Vhat = R (A - S conj(H) Xi'), HVhat = S H Vhat  (admm.py:280-294, 320)
-    C2R(Vhat) -> V, C2R(HVhat) -> HV
+    B1  row IFFT of the (V, HV) row spectra                            -> V, HV
+    B2  fused spatial pass -- dual completion, U/X/W proxes, new half-duals, FFT operand a
+        (admm.py:232-263, 277-279, 298-311) -> row FFT                 -> row spectra of (a, xi')
+    A   persistent TMA-pipelined column kernel: column FFT -> Vhat = R (A - S conj(H) Xi'),
+        HVhat = S H Vhat (admm.py:280-294, 320; R evaluated on the fly) -> column IFFT
 
-see lenslesspicam_b200/csrc/lpc_admm.cuh and DESIGN.md.
+Other sizes / fp64 / ``engine="v1"`` run K1 (spatial) + cuFFT + K2 (spectral).
+See lenslesspicam_b200/csrc/lpc_fused.cuh, lpc_fused_tma.cuh, lpc_admm.cuh and DESIGN.md.
 """
 import time
 

@@ -2,9 +2,11 @@
 GPU mirrors of ``lensless.GradientDescent`` / ``NesterovGradientDescent`` / ``FISTA``
 (reference: lensless/recon/gd.py:62-241), projection = non-negativity.
 
-Per iteration: 4 cuFFT transforms + 4 kernels (2 spectral multiplies carrying H /
-conj(H) and the ifftshift phase, the residual crop(Hx) - y, and the fused
-step + projection + momentum update); see lenslesspicam_b200/csrc/lpc_gd.cuh.
+Per iteration the fused engine (fp32, menu sizes) runs four hand-written kernels that own their FFTs:
+columns(H) -> rows(crop, - y, zero-pad) -> columns(conj H) -> rows(step + projection + momentum); only the
+window rows of the zero-padded problem are ever transformed along rows, stored or loaded
+(lenslesspicam_b200/csrc/lpc_fused_gd.cuh, lpc_fused_tma.cuh).  Other sizes / fp64 run cuFFT + four
+kernels (lpc_gd.cuh).
 """
 import inspect
 
