@@ -411,7 +411,7 @@ def main():
         },
     }
     line = {
-        "metric": (METRIC if (args.algo == "admm" and D == 1 and n_iter == 100) else
+        "metric": (METRIC if (args.algo == "admm" and D == 1 and n_iter == 100 and (h, w, C) == (1080, 1920, 3)) else
                    f"{args.algo.upper()}-{n_iter} reconstructions/sec @ {str(D) + 'x' if D > 1 else ''}{C}x{h}x{w}"),
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -41,14 +41,14 @@ constexpr int LPC_ROWS_THREADS = 256;
 constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIANT=1) uses 576 threads x 2 CTAs/SM
 
 // padded sizes with a compiled fast path: X(N, radices...).  Rows = Wp, columns = Hp.
-// 3840x2160: 1080x1920 (headline); 2048x1536 / 1024x768 / 512x384: the bundled 3040x4056 data at
-// downsample 4 / 8 / 16; the small ones are the shapes of tests/golden (odd, mixed, gray).
+// 3840x2160: 1080x1920 (headline); 1920x1080 / 960x540: 540x960 and 270x480 (the DiffuserCam dataset's size);
+// 2048x1536 / 1024x768 / 512x384: the bundled 3040x4056 data at downsample 4 / 8 / 16; the small ones are the shapes of tests/golden (odd, mixed, gray).
 #define LPC_ROW_MENU(X) \
-    X(3840, 15, 16, 16) X(2048, 16, 16, 8) X(1024, 16, 16, 4) X(512, 16, 8, 4) X(480, 15, 16, 2) \
+    X(3840, 15, 16, 16) X(2048, 16, 16, 8) X(1920, 15, 16, 8) X(1024, 16, 16, 4) X(960, 15, 16, 4) X(512, 16, 8, 4) X(480, 15, 16, 2) \
     X(288, 9, 16, 2) X(125, 5, 5, 5) X(75, 15, 5) X(64, 16, 4) X(54, 9, 6)
 // (column sequences end in a small radix: that pass is fused with the spectral update in registers)
 #define LPC_COL_MENU(X) \
-    X(2160, 15, 16, 9) X(1536, 12, 16, 8) X(768, 16, 16, 3) X(384, 16, 8, 3) X(405, 15, 9, 3) \
+    X(2160, 15, 16, 9) X(1536, 12, 16, 8) X(1080, 8, 15, 9) X(768, 16, 16, 3) X(540, 4, 15, 9) X(384, 16, 8, 3) X(405, 15, 9, 3) \
     X(270, 15, 9, 2) X(200, 5, 8, 5) X(48, 16, 3) X(45, 15, 3) X(40, 5, 8) X(27, 9, 3)
 
 struct FusedK {

@@ -219,12 +219,13 @@ def test_fused_engine_is_default_and_agrees_with_cufft_engine(case):
 
 
 # ------------------------------------------------------------------------------ live oracle parity
-@pytest.mark.parametrize("shape", [(135, 240, 3), (203, 61, 3), (100, 136, 1)])
+@pytest.mark.parametrize("shape", [(135, 240, 3), (203, 61, 3), (100, 136, 1), (270, 480, 3)])
 def test_parity_with_oracle_mid_size(shape):
     """BASELINE config 1's ~3x135x240 class, an odd-padded shape and a gray one, seeded inputs"""
     h, w, C = shape
     psf, data = orc.synthetic_problem(h, w, C, seed=11)
-    for algo, n in (("admm", 20), ("fista", 20), ("gd", 10), ("nesterov", 10)):
+    n_admm = 8 if shape[0] >= 270 else 20  # fp32 round-off of ADMM grows with size x iterations (see the envelope rule below)
+    for algo, n in (("admm", n_admm), ("fista", 20), ("gd", 10), ("nesterov", 10)):
         res, _ = run(algo, psf, data, n)
         out = res.cpu().numpy()
         ref = orc.reconstruct(algo, psf, data, n)
@@ -238,6 +239,7 @@ def test_parity_with_oracle_mid_size(shape):
         # fp32 reference than the two fp32 round-off clouds explain.
         ref64 = orc.reconstruct(algo, psf, data, n, dtype="float64")
         e64, e3264 = rel_to_max(out, ref64), rel_to_max(ref, ref64)
+        # (at 270x480x3 and 20 iterations: reference fp32 vs fp64 2.1e-5, ours vs fp64 1.2e-5 -- neither inside 1e-5)
         assert e64 <= TOL and e32 <= e64 + e3264, (shape, algo, e32, e64, e3264)
 
 
