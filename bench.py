@@ -4,9 +4,9 @@ bench.py -- BASELINE.json's metric: 100-iteration ADMM reconstructions / second 
 3x1080x1920 (padded 2160x3840) DiffuserCam-shape measurements, fp32.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our engine
-    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (oracle port)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the UNMODIFIED reference's CPU path (baseline/_ref)
 
-A "step" is one complete reconstruction of one measurement per GPU:
+A "step" of our arm is one complete reconstruction of one measurement per GPU:
 set_data -> reset -> 100 x _update -> crop/clamp image.  With N > 1 (launched by torchrun, one
 rank per GPU) the batch axis is sharded: every rank reconstructs its own measurement per step
 (weak scaling); the PSF is broadcast once over NCCL at init and there is no collective inside
@@ -16,13 +16,24 @@ value     : whole-job recon/s with the measurement already resident in HBM (devi
             CUDA events, max over ranks).
 e2e       : same metric through the host-buffer call (pinned host measurement -> H2D ->
             recon -> D2H image) with the copies inside the timed region.
-roofline  : our dominant kernel (the longest launch of the iteration: the fused spatial-update + row-FFT
-            kernel B2), algorithmic bytes / CUDA-event duration measured live via lpc_profile(),
-            against MEASURED_PEAKS.json.
-cpu_baseline : the numpy oracle port of the reference, timed on this box's host cores on a
-            bounded sample (a few iterations at full size, scaled to 100).
+roofline  : our dominant kernel (the longest launch of the iteration), algorithmic bytes / CUDA-event
+            duration measured live via lpc_profile(), against MEASURED_PEAKS.json.
+configs   : the other BASELINE.json configurations, each timed the same way in the same run:
+            fista300 (configs[2]), bundled_ds8_admm5 / joss_ds4_gray (configs[0] and the JOSS paper's table),
+            depth16_admm50 (configs[4]), batch256 (configs[3]: 256 host-resident measurements through
+            lenslesspicam_b200.dist.reconstruct_sharded, time-to-solution -> strong scaling over N).
+parity    : N = 1 only -- ours vs the reference's torch path run on the same GPU in fp64 (truth) and fp32
+            (trajectory) for ADMM-100 and FISTA-300 at the headline shape (checker, not measured).
+cpu_baseline / torch_baseline_gpu : the unmodified reference (baseline/_ref) on this box's host cores (numpy path as
+            shipped, bounded sample) and on the same GPU (torch path, explicit synchronisation); the oracle port
+            stands in only when baseline/_ref is absent.
+
+The reference arm (--impl reference): one step = ONE full-size iteration (`_update`, recon.py:575-576) of the
+unmodified reference's numpy path with every host thread given to scipy.fft; `ms_per_step` is that iteration's
+real duration and `value` scales it to n_iter (per-iteration cost is constant).
 """
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -52,10 +63,45 @@ def parse():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--depth", type=int, default=1, help="PSF depth D > 1: BASELINE configs[4], D independent 2-D problems "
                     "against one measurement (ADMM(allow_depth=True); the reference has no 3-D ADMM, SURVEY 8a note)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="default", help="'default' = every BASELINE config next to the headline when the "
+                    "headline shape is benchmarked, 'none', or a comma list of fista300,bundled,depth16,batch256")
+    ap.add_argument("--batch256-n", type=int, default=256, help="measurements of the sharded-batch config (BASELINE configs[3])")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline / torch_baseline_gpu / parity")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--engine", default=None, choices=[None, "v1"], help="v1 = K1/K2 + cuFFT (A/B against the fused engine)")
     return ap.parse_args()
+
+
+def next_fast_len(n):
+    """smallest 5-smooth integer >= n (scipy.fftpack.next_fast_len, rfft_convolve.py:16,112)"""
+    best = None
+    p5 = 1
+    while p5 < 2 * n:
+        p35 = p5
+        while p35 < 2 * n:
+            c = p35
+            while c < n:
+                c *= 2
+            best = c if best is None or c < best else best
+            p35 *= 3
+        p5 *= 5
+    return best if n > 6 else max(n, 0)
+
+
+def workload(algo, n_iter, C, h, w, D=1):
+    """config.workload -- the SAME string for both arms (the driver compares them)"""
+    Hp, Wp = next_fast_len(2 * h - 1), next_fast_len(2 * w - 1)
+    if D == 1:
+        return (f"{algo.upper()} n_iter={n_iter} fp32, single {C}x{h}x{w} measurement per GPU per step "
+                f"(BASELINE configs[{1 if algo == 'admm' else 2}]), padded {Hp}x{Wp}")
+    return (f"{algo.upper()} n_iter={n_iter} fp32, {D}-depth PSF stack x {C}x{h}x{w}, one measurement per GPU per step (BASELINE "
+            f"configs[4]: {D} independent 2-D problems against the same measurement -- the reference has no 3-D ADMM), padded {Hp}x{Wp}")
+
+
+def metric_name(algo, n_iter, C, h, w, D=1):
+    if algo == "admm" and D == 1 and n_iter == 100 and (h, w, C) == (1080, 1920, 3):
+        return METRIC
+    return f"{algo.upper()}-{n_iter} reconstructions/sec @ {str(D) + 'x' if D > 1 else ''}{C}x{h}x{w}"
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -126,109 +172,217 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ----------------------------------------------------------------------------------------- reference arm
-def run_reference(args, out):
-    """The reference's own CPU implementation of the path: the numpy oracle port (the reference is
-    pure Python and cannot travel to the GPU box), all host threads given to pocketfft.
-    One step = ONE full-size iteration (a bounded sample); value scales it to n_iter."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def load_reference():
+    """the UNMODIFIED reference from baseline/_ref (None when it was not installed)"""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_loader
+
+        return ref_loader.load()
+    except Exception:
+        return None
+
+
+def synthetic_numpy(h, w, C, seed=0):
     import numpy as np
 
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lensless_oracle as orc
-
-    n_iter = args.n_iter or (100 if args.algo == "admm" else 300)
-    cores = os.cpu_count() or 1
-    h, w, C = args.height, args.width, args.channels
-    rng = np.random.default_rng(0)
+    rng = np.random.default_rng(seed)
     psf = (rng.random((1, h, w, C)) ** 8).astype(np.float32)
     psf /= np.linalg.norm(psf.ravel())
     data = rng.random((1, h, w, C)).astype(np.float32)
-    solver = orc.ALGOS[args.algo](psf, dtype="float32", workers=cores)
-    solver.set_data(data)
-    solver.reset()
-    for _ in range(args.warmup):
-        solver.update()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        solver.update()
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    return psf, data
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def run_reference(args, out):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # under torchrun only rank 0 works; the others exit 0
+    n_iter = args.n_iter or (100 if args.algo == "admm" else 300)
+    cores = os.cpu_count() or 1
+    h, w, C = args.height, args.width, args.channels
+    psf, data = synthetic_numpy(h, w, C)
+    ref = load_reference()
+    if ref is not None:
+        from scipy import fft as sfft
+
+        kind = "reference"
+        cls = ref.ADMM if args.algo == "admm" else ref.FISTA
+        solver = cls(psf, dtype="float32")
+        solver.set_data(data)
+        ctx = sfft.set_workers(cores)  # scipy.fft's own global knob: the reference code itself is untouched
+        step = lambda i: solver._update(i)  # noqa: E731  (the loop body of apply(), recon.py:575-576)
+        what = "unmodified reference (baseline/_ref) numpy path, scipy.fft.set_workers(all cores)"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lensless_oracle as orc
+
+        kind = "port"
+        solver = orc.ALGOS[args.algo](psf, dtype="float32", workers=cores)
+        solver.set_data(data)
+        solver.reset()
+        ctx = contextlib.nullcontext()
+        step = lambda i: solver.update()  # noqa: E731
+        what = "numpy + scipy.fft oracle port (baseline/_ref absent), all cores"
+    with ctx:
+        for i in range(args.warmup):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = 1.0 / (dt * n_iter)
-    sample = f"{args.steps} timed full-size iterations after {args.warmup} warm-up, scaled x{n_iter} (per-iteration cost is constant)"
+    sample = (f"one step = ONE full-size iteration ({what}); {args.steps} timed after {args.warmup} warm-up; "
+              f"value = 1 / (ms_per_step x {n_iter} iterations): the per-iteration cost is constant")
+    extra = {}
+    if ref is not None and args.algo in ("admm", "fista"):
+        try:  # the reference's torch-CPU path, every intra-op thread (the faster of its two CPU paths on most hosts)
+            import torch
+
+            torch.set_num_threads(cores)
+            cls = ref.ADMM if args.algo == "admm" else ref.FISTA
+            ts = cls(torch.from_numpy(psf), dtype="float32")
+            ts.set_data(torch.from_numpy(data))
+            ts._update(0)
+            t0 = time.perf_counter()
+            for i in range(3):
+                ts._update(1 + i)
+            dtt = (time.perf_counter() - t0) / 3
+            extra["torch_cpu"] = {"value": 1.0 / (dtt * n_iter), "unit": UNIT, "s_per_iter": dtt, "threads": cores,
+                                  "sample": "3 timed full-size iterations after 1 warm-up, unmodified reference torch-CPU path"}
+        except Exception as e:
+            extra["torch_cpu"] = {"unavailable": repr(e)[:200]}
     line = {
         "impl": "reference",
-        "metric": METRIC if args.algo == "admm" else f"FISTA-{n_iter} reconstructions/sec @ 3x1080x1920",
+        "metric": metric_name(args.algo, n_iter, C, h, w),
         "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * n_iter * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.algo.upper()} n_iter={n_iter} fp32, single {C}x{h}x{w} measurement (BASELINE configs[1]), numpy+scipy.fft oracle port of lensless/recon"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload(args.algo, n_iter, C, h, w), "step": "one iteration of the workload (bounded sample)",
+                   "iterations_per_reconstruction": n_iter},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "s_per_iter": dt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        **extra,
     }
     out.emit(json.dumps(line))
 
 
 def cpu_baseline(args, n_iter):
-    """numpy oracle AS SHIPPED by the reference (scipy.fft with 1 thread), bounded sample."""
-    import numpy as np
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lensless_oracle as orc
-
+    """The reference's numpy path AS SHIPPED (scipy.fft with its default single thread), bounded sample."""
     h, w, C = args.height, args.width, args.channels
-    rng = np.random.default_rng(0)
-    psf = (rng.random((1, h, w, C)) ** 8).astype(np.float32)
-    psf /= np.linalg.norm(psf.ravel())
-    data = rng.random((1, h, w, C)).astype(np.float32)
-    solver = orc.ALGOS[args.algo](psf, dtype="float32", workers=None)
-    solver.set_data(data)
-    solver.reset()
-    solver.update()
+    psf, data = synthetic_numpy(h, w, C)
+    ref = load_reference()
+    if ref is not None:
+        cls = ref.ADMM if args.algo == "admm" else ref.FISTA
+        solver = cls(psf, dtype="float32")
+        solver.set_data(data)
+        step, kind = (lambda i: solver._update(i)), "reference"
+        what = "unmodified reference (baseline/_ref), numpy + scipy.fft as shipped (1 FFT thread)"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lensless_oracle as orc
+
+        solver = orc.ALGOS[args.algo](psf, dtype="float32", workers=None)
+        solver.set_data(data)
+        solver.reset()
+        step, kind = (lambda i: solver.update()), "port"
+        what = "numpy + scipy.fft oracle port (1 FFT thread)"
+    step(0)
     k = 3
     t0 = time.perf_counter()
-    for _ in range(k):
-        solver.update()
+    for i in range(k):
+        step(1 + i)
     dt = (time.perf_counter() - t0) / k
     return {
-        "value": 1.0 / (dt * n_iter), "unit": UNIT, "cores": 1, "kind": "port",
-        "sample": f"{k} timed full-size iterations after 1 warm-up, scaled x{n_iter}; numpy + scipy.fft (pocketfft, 1 thread as the reference ships it); host has {os.cpu_count()} cores",
+        "value": 1.0 / (dt * n_iter), "unit": UNIT, "cores": 1, "kind": kind,
+        "sample": f"{k} timed full-size iterations after 1 warm-up, scaled x{n_iter}; {what}; host has {os.cpu_count()} cores "
+                  "(the all-cores figure is the --impl reference arm)",
         "s_per_iter": dt,
     }
 
 
-def torch_baseline_gpu(args, n_iter, device, psf, meas):
-    """The reference's TORCH path on the SAME GPU (BASELINE.md section 3, item 5: 'the real bar for the fused
-    kernels'): oracle/lensless_oracle_torch.py restates lensless/recon/{admm,gd}.py's torch branch operation for
-    operation (pinned against the reference's torch outputs in tests/); timed with explicit synchronisation on a
-    bounded sample and scaled to n_iter."""
+def reference_gpu_solver(algo, psf, dtype):
+    """the reference's torch path on the GPU: the unmodified class from baseline/_ref, else the restatement"""
     import torch
 
+    ref = load_reference()
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    if ref is not None:
+        cls = ref.ADMM if algo == "admm" else ref.FISTA
+        return cls(psf.to(tdt), dtype=dtype), "reference"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import lensless_oracle_torch as ot
 
-    solver = ot.ALGOS[args.algo](psf)
-    solver.set_data(meas[:1])
-    solver.reset()
-    for _ in range(3):
-        solver.update()
-    k = 10
+    class _Wrap:
+        def __init__(self):
+            self.s = ot.ALGOS[algo](psf.to(tdt))
+
+        def set_data(self, d):
+            self.s.set_data(d)
+
+        def apply(self, n_iter, **kw):
+            return self.s.apply(n_iter)
+
+    return _Wrap(), "port"
+
+
+def torch_baseline_gpu(args, n_iter, device, psf, meas):
+    """The reference's TORCH path on the SAME GPU (BASELINE.md section 3, item 5: 'the real bar for the fused
+    kernels'), as profile/admm.py:93-108 runs it but WITH torch.cuda.synchronize(): full apply(n_iter) calls."""
+    import torch
+
+    solver, kind = reference_gpu_solver(args.algo, psf, "float32")
+    solver.set_data(meas[0])
+    solver.apply(n_iter=3, disp_iter=None, plot=False)
     torch.cuda.synchronize(device)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    k = 2
+    t0 = time.perf_counter()
     for _ in range(k):
-        solver.update()
-    e1.record()
+        solver.apply(n_iter=n_iter, disp_iter=None, plot=False)
     torch.cuda.synchronize(device)
-    ms = e0.elapsed_time(e1) / k
+    s = (time.perf_counter() - t0) / k
     del solver
     torch.cuda.empty_cache()
     return {
-        "value": 1.0 / (ms * 1e-3 * n_iter), "unit": UNIT, "kind": "port (torch ops of the reference's torch branch, same GPU)",
-        "ms_per_iter": ms, "sample": f"{k} timed full-size iterations after 3 warm-up, CUDA events + synchronize, scaled x{n_iter}",
+        "value": 1.0 / s, "unit": UNIT, "kind": kind + " (lensless torch path, same GPU)", "ms_per_recon": s * 1e3,
+        "ms_per_iter": s * 1e3 / n_iter,
+        "sample": f"{k} full apply(n_iter={n_iter}) calls after a 3-iteration warm-up, wall clock between torch.cuda.synchronize()",
     }
+
+
+def parity_block(L, device, psf, meas, configs):
+    """ours vs the reference's torch path on this GPU in fp64 (truth) and fp32 (trajectory), rel-to-max errors"""
+    import torch
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+    out = {}
+    for algo, n in configs:
+        try:
+            cls = L.ADMM if algo == "admm" else L.FISTA
+            rec = cls(psf)
+            rec.set_data(meas[:1])
+            mine = rec.apply(n_iter=n, disp_iter=None, plot=False)
+            del rec
+            res = {}
+            for dt in ("float64", "float32"):
+                solver, kind = reference_gpu_solver(algo, psf, dt)
+                solver.set_data(meas[0].to(torch.float64 if dt == "float64" else torch.float32))
+                res[dt] = solver.apply(n_iter=n, disp_iter=None, plot=False).clone()
+                del solver
+                torch.cuda.empty_cache()
+            out[f"{algo}-{n}"] = {
+                "ours_vs_fp64": rel(mine, res["float64"]), "ref32_vs_fp64": rel(res["float32"], res["float64"]),
+                "ours_vs_ref32": rel(mine, res["float32"]), "truth": kind + " torch path, fp64, same GPU", "metric": "max|a-b|/max|b|",
+            }
+            del mine, res
+        except Exception as e:
+            out[f"{algo}-{n}"] = {"unavailable": repr(e)[:200]}
+        torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------- stdout hygiene
@@ -255,8 +409,8 @@ def main():
 
     import ctypes
 
+    import numpy as np
     import torch
-    import torch.distributed as dist
 
     import lenslesspicam_b200 as L
     from lenslesspicam_b200 import _lib
@@ -266,34 +420,83 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     lpd.init(backend="nccl", device=device)
+    lib = _lib.load()
+    peak, peak_src = measured_peaks()
 
     n_iter = args.n_iter or (100 if args.algo == "admm" else 300)
     h, w, C, Bg = args.height, args.width, args.channels, args.batch_per_gpu
-
-    # ---- synthetic inputs: PSF on rank 0, broadcast once over NCCL; per-rank scenes
     D = args.depth
-    gen = torch.Generator().manual_seed(0)
-    psf = torch.rand((D, h, w, C), generator=gen) ** 8
-    psf = (psf / psf.norm()).to(device)
-    if world > 1 and rank != 0:
-        psf.zero_()
-    lpd.broadcast_psf(psf, src=0)  # the only collective of the job: init-time, NCCL over NVLink/NVSwitch
-    gen = torch.Generator().manual_seed(1000 + rank)
-    scene = (torch.rand((Bg, 1, h, w, C), generator=gen) ** 2).to(device)
-    if D == 1:
-        sim = L.RealFFTConvolve2D(psf, pad=True, norm="backward")
-        meas = sim.convolve(scene).clamp_(min=0)
-        meas = meas / meas.amax(dim=(1, 2, 3, 4), keepdim=True)
-        del sim
+    headline = (args.algo == "admm" and D == 1 and n_iter == 100 and (h, w, C, Bg) == (1080, 1920, 3, 1) and args.engine is None)
+    if args.configs == "default":
+        want = {"fista300", "bundled", "depth16", "batch256"} if headline else set()
+    elif args.configs == "none":
+        want = set()
     else:
-        meas = scene  # the arithmetic is data-independent except clamps / thresholds: any measurement times the same
-    del scene
-    host_in = meas.cpu().pin_memory()
-    host_out = torch.empty((Bg, D, h, w, C), dtype=torch.float32).pin_memory()
+        want = {c.strip() for c in args.configs.split(",") if c.strip()}
 
-    cls = L.ADMM if args.algo == "admm" else L.FISTA
     stream = torch.cuda.Stream(device=device)
+
+    def barrier():
+        lpd.barrier(device)
+
+    def timed(fn, K):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            fn()
+        e1.record(stream)
+        barrier()
+        return lpd.max_over_ranks(e0.elapsed_time(e1), device=device)
+
+    def make_problem(D_, h_, w_, C_, B_, seed_psf=0):
+        """synthetic inputs: PSF on rank 0, broadcast once over NCCL; per-rank scenes"""
+        gen = torch.Generator().manual_seed(seed_psf)
+        psf_ = torch.rand((D_, h_, w_, C_), generator=gen) ** 8
+        psf_ = (psf_ / psf_.norm()).to(device)
+        if world > 1 and rank != 0:
+            psf_.zero_()
+        lpd.broadcast_psf(psf_, src=0)  # the only collective of the job: init-time, NCCL over NVLink/NVSwitch
+        gen = torch.Generator().manual_seed(1000 + rank)
+        scene = (torch.rand((B_, 1, h_, w_, C_), generator=gen) ** 2).to(device)
+        if D_ == 1:
+            sim = L.RealFFTConvolve2D(psf_, pad=True, norm="backward")
+            meas_ = sim.convolve(scene).clamp_(min=0)
+            meas_ = meas_ / meas_.amax(dim=(1, 2, 3, 4), keepdim=True)
+            del sim
+        else:
+            meas_ = scene  # the arithmetic is data-independent except clamps / thresholds: any measurement times the same
+        return psf_, meas_
+
+    def bench_config(algo, psf_, meas_, n_it, steps, warm=3, **extra):
+        """device-resident recon/s of one configuration, same timing rules as the headline"""
+        cls = L.ADMM if algo == "admm" else L.FISTA
+        rec = cls(psf_, n_iter=n_it, **extra)
+
+        def step():
+            rec.set_data(meas_)
+            return rec.apply(disp_iter=None, plot=False)
+
+        for _ in range(warm):
+            step()
+        ms = timed(step, steps)
+        bpi = rec.bytes_per_iter()
+        eng = rec.engine_version
+        B_ = int(meas_.shape[0])
+        del rec
+        torch.cuda.empty_cache()
+        ms_step = ms / steps
+        gbs = bpi * n_it / (ms_step * 1e-3) / 1e9
+        return {"value": world * B_ * 1e3 / ms_step, "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warm,
+                "n_iter": n_it, "engine_version": eng,
+                "roofline": {"bound": "hbm", "algorithmic_bytes_per_iter": bpi, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak}}
+
     with torch.cuda.stream(stream):
+        psf, meas = make_problem(D, h, w, C, Bg)
+        host_in = meas.cpu().pin_memory()
+        host_out = torch.empty((Bg, D, h, w, C), dtype=torch.float32).pin_memory()
+
+        cls = L.ADMM if args.algo == "admm" else L.FISTA
         extra = {"allow_depth": True} if (D > 1 and args.algo == "admm") else {}
         recon = cls(psf, n_iter=n_iter, no_graph=args.no_graph, engine=args.engine, **extra)
 
@@ -304,19 +507,6 @@ def main():
         def step_host():
             recon.apply_host(host_in, host_out, n_iter=n_iter)
             stream.synchronize()  # the caller reads the image: a real end-to-end step ends on the host
-
-        def barrier():
-            lpd.barrier(device)
-
-        def timed(fn, K):
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(K):
-                fn()
-            e1.record(stream)
-            barrier()
-            return lpd.max_over_ranks(e0.elapsed_time(e1), device=device)
 
         for _ in range(max(args.warmup, 3)):
             step_device()
@@ -341,14 +531,73 @@ def main():
         recon.apply(n_iter=2, disp_iter=None)
         phase_ms = (ctypes.c_double * 8)()
         nph = ctypes.c_int()
-        lib = _lib.load()
         _lib.check(lib.lpc_profile(recon._plan, 10, stream.cuda_stream, phase_ms, ctypes.byref(nph)), recon._plan)
-        algo_code = _lib.ALGO_ADMM if args.algo == "admm" else _lib.ALGO_FISTA
         phases = {}
         for i in range(nph.value):
             name = lib.lpc_phase_name(recon._plan, i).decode()
             phases[name] = phases.get(name, 0.0) + phase_ms[i]
         bytes_iter = recon.bytes_per_iter()
+        # non-iteration share of a reconstruction: pack (set_data), reset memsets, crop/clamp (get_image), graph launch
+        ov = {}
+        for name, fn in (("set_data(pack)", lambda: recon._send_data()), ("reset", recon.reset), ("form_image(crop+clamp)", recon._form_image)):
+            fn()
+            ov[name] = timed(fn, 5) / 5
+        engine = lib.lpc_engine_version(recon._plan)
+        _, Hp, Wp, _ = recon._padded_shape
+
+        # ---- the other BASELINE configurations, same run
+        cfgs = {}
+        if "fista300" in want:
+            cfgs["fista300"] = bench_config("fista", psf, meas, 300, 3)
+            cfgs["fista300"]["workload"] = workload("fista", 300, C, h, w)
+        if "bundled" in want:
+            for key, fname in (("bundled_ds8", "bundled_ds8.npz"), ("joss_ds4_gray", "bundled_ds4_gray.npz")):
+                fp = os.path.join(ROOT, "tests", "golden", fname)
+                if not os.path.exists(fp):
+                    continue
+                g = np.load(fp)
+                bp, bd = torch.from_numpy(g["psf"]).to(device), torch.from_numpy(g["data"]).to(device)[None]
+                shape = "x".join(str(v) for v in (bp.shape[3], bp.shape[1], bp.shape[2]))
+                for algo_, n_ in (("admm", 5), ("fista", 300)):
+                    r = bench_config(algo_, bp, bd, n_, 10)
+                    r["workload"] = (f"{algo_.upper()} n_iter={n_} fp32 on the reference's bundled tape PSF / thumbs-up measurement, {shape} "
+                                     f"({'load_data(downsample=8), BASELINE configs[0]' if key == 'bundled_ds8' else 'downsample=4 gray: profile/admm.py:12-16, the JOSS paper table'})")
+                    cfgs[f"{key}_{algo_}{n_}"] = r
+                del bp, bd
+        if "depth16" in want:
+            dp, dm = make_problem(16, h, w, 1, 1, seed_psf=7)
+            cfgs["depth16_admm50"] = bench_config("admm", dp, dm, 50, 3, allow_depth=True)
+            cfgs["depth16_admm50"]["workload"] = workload("admm", 50, 1, h, w, D=16)
+            del dp, dm
+        del recon
+        torch.cuda.empty_cache()
+        if "batch256" in want:
+            # BASELINE configs[3]: N host-resident measurements, batch axis sharded over the ranks, every measurement
+            # copied H2D and its image D2H inside the timed region; time-to-solution = max over ranks
+            NB = args.batch256_n
+            gen = torch.Generator().manual_seed(77)
+            base = meas[0:1].cpu()
+            host_batch = torch.empty((NB, 1, h, w, C), dtype=torch.float32).pin_memory()
+            for i in range(NB):  # distinct measurements (a cheap roll of a synthetic one); identical on every rank
+                host_batch[i] = torch.roll(base[0], shifts=(7 * i) % h, dims=1)
+            solver = L.ADMM(psf, n_iter=100)
+            lpd.reconstruct_sharded(host_batch[: 2 * world], psf, n_iter=100, solver=solver)  # warm-up: plans, graphs
+            barrier()
+            t0 = time.perf_counter()
+            local_out, mine = lpd.reconstruct_sharded(host_batch, psf, n_iter=100, solver=solver)
+            torch.cuda.synchronize(device)
+            dt_ms = lpd.max_over_ranks((time.perf_counter() - t0) * 1e3, device=device)
+            bpi = 100 * solver.bytes_per_iter()  # per image (plans of batch 1)
+            cfgs["batch256"] = {
+                "value": NB * 1e3 / dt_ms, "unit": UNIT, "time_to_solution_ms": dt_ms, "measurements": NB, "per_gpu": len(mine),
+                "scaling": "strong", "h2d_bytes": int(NB * 4 * h * w * C), "d2h_bytes": int(NB * 4 * h * w * C),
+                "workload": f"ADMM n_iter=100, batch={NB} synthetic {C}x{h}x{w} host-resident measurements sharded across {world} GPU(s) "
+                            "(BASELINE configs[3]) through lenslesspicam_b200.dist.reconstruct_sharded; host wall clock around the call, max over ranks",
+                "roofline": {"bound": "hbm", "achieved": NB * bpi / (dt_ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
+                             "frac": NB * bpi / (dt_ms * 1e-3) / 1e9 / world / peak},
+            }
+            del solver, host_batch, local_out
+            torch.cuda.empty_cache()
 
     if rank != 0:
         lpd.finalize()
@@ -358,9 +607,7 @@ def main():
     ms_step = ms_dev / args.steps
     value = total * args.steps / (ms_dev / 1e3)
     e2e_value = total * args.steps / (ms_e2e / 1e3)
-    peak, peak_src = measured_peaks()
 
-    _, Hp, Wp, _ = recon._padded_shape
     P = 4.0 * Bg * D * Hp * Wp * C
     Sp = 8.0 * Bg * D * Hp * (Wp // 2 + 1) * C
     d = 4.0 * Bg * D * h * w * C
@@ -383,7 +630,6 @@ def main():
     own = {n: t for n, t in phases.items() if n in kernel_bytes}
     kname = max(own, key=own.get)  # our dominant kernel = the one with the longest launch
     kbytes = kernel_bytes[kname]
-    engine = lib.lpc_engine_version(recon._plan)
     if args.algo == "admm":
         own_launches = (3 if engine == 2 else 2) * n_iter + 2  # kernels / iteration, pack + unpack per recon
     else:
@@ -403,24 +649,22 @@ def main():
         "algorithmic_bytes_per_launch": kbytes, "launch_ms": k_ms,
         "phases_ms_per_iter": phases,
         "phases_GBs": {n: kernel_bytes[n] / (t * 1e-3) / 1e9 for n, t in own.items() if t > 0},
+        "phases_frac": {n: kernel_bytes[n] / (t * 1e-3) / 1e9 / peak for n, t in own.items() if t > 0},
         "engine": "v2 fused own-FFT (3 kernels / iteration)" if engine == 2 else "v1 K1/K2 + cuFFT",
         "iteration": {
             "algorithmic_bytes": bytes_iter, "ms_ungraphed": iter_ms, "ms_in_step": ms_step / n_iter / Bg,
             "achieved_GBs": bytes_iter / (ms_step / n_iter * 1e-3) / 1e9,
             "frac_of_peak": bytes_iter / (ms_step / n_iter * 1e-3) / 1e9 / peak,
         },
+        "per_recon_overhead_ms": {**ov, "iterations(graph)": ms_step - sum(ov.values()), "step": ms_step},
     }
     line = {
-        "metric": (METRIC if (args.algo == "admm" and D == 1 and n_iter == 100 and (h, w, C) == (1080, 1920, 3)) else
-                   f"{args.algo.upper()}-{n_iter} reconstructions/sec @ {str(D) + 'x' if D > 1 else ''}{C}x{h}x{w}"),
+        "metric": metric_name(args.algo, n_iter, C, h, w, D),
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": (f"{args.algo.upper()} n_iter={n_iter} fp32, single {C}x{h}x{w} measurement per GPU per step (BASELINE configs[1]), padded {Hp}x{Wp}"
-                         if D == 1 else
-                         f"{args.algo.upper()} n_iter={n_iter} fp32, {D}-depth PSF stack x {C}x{h}x{w}, one measurement per GPU per step (BASELINE configs[4]: "
-                         f"{D} independent 2-D problems against the same measurement -- the reference has no 3-D ADMM), padded {Hp}x{Wp}"),
+            "workload": workload(args.algo, n_iter, C, h, w, D),
             "batch_per_gpu": Bg, "parallelism": f"batch-sharded x{world}, PSF broadcast once (NCCL), no collective in the iteration",
             "l2": "per-recon working set ~1.4 GB >> 126 MB L2 (inputs larger than L2; no explicit flush)",
             "cuda_graph": not args.no_graph,
@@ -432,6 +676,7 @@ def main():
         "gpu_launches": own_launches * args.steps,  # our kernels inside the `value` timed region (cuFFT kernels not counted)
         "roofline": roofline,
         "clocks": clocks,
+        "configs": cfgs,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, n_iter)
@@ -440,6 +685,8 @@ def main():
                 line["torch_baseline_gpu"] = torch_baseline_gpu(args, n_iter, device, psf, meas)
             except Exception as e:  # never lose the bench line to the extra baseline
                 line["torch_baseline_gpu"] = {"unavailable": repr(e)[:200]}
+            if headline:
+                line["parity"] = parity_block(L, device, psf, meas, (("admm", 100), ("fista", 300)))
     out.emit(json.dumps(line))
     lpd.finalize()
 

@@ -74,6 +74,16 @@ extern "C" {
 #define LPC_FLAG_NONE 0
 #define LPC_FLAG_NO_GRAPH 1   /* never capture the iteration loop in a CUDA graph        */
 #define LPC_FLAG_ENGINE_V1 4  /* K1/K2/K3 + cuFFT engine instead of the fused own-FFT engine (A/B, bisecting) */
+#define LPC_FLAG_PSF_PER_SAMPLE 8 /* the plan holds ONE PSF PER BATCH ENTRY: lpc_set_psf takes [B,D,h,w,C]; H, R_divmat,
+                                     alpha and the initial value are per sample (multi-mask batches: the reference's
+                                     forward(batch, psfs) builds RealFFTConvolve2D(psfs[B,...]), trainable_recon.py:347-350;
+                                     eval/benchmark.py:186-190,255-259) */
+
+/* lpc_set_option selectors */
+#define LPC_OPT_KEEP_X0 1      /* != 0: lpc_set_psf keeps the GD-family initial value (psf min/max, gd.py:99-105) of the
+                                  PSF set BEFORE: UnrolledFISTA.forward(psfs) swaps the convolver only, its _image_init
+                                  stays the constructor PSF's (trainable_recon.py:347-350, unrolled_fista.py:55-59) */
+#define LPC_OPT_B2_PREFETCH 2  /* tuning: L2-prefetch distance (rows) of the fused spatial kernel, 0 = off */
 
 typedef struct lpc_plan_s* lpc_plan_t;
 
@@ -105,7 +115,7 @@ int lpc_plan_destroy(lpc_plan_t plan);
 /* RealFFTConvolve2D.set_psf (rfft_convolve.py:102-131): pad PSF, H = rfft2(.)*norm,
  * plus the algorithm constants derived from H: ADMM R_divmat (admm.py:186-190),
  * GD step alpha and initial estimate (gd.py:96-112).  dev_psf is [D,h,w,C]. */
-int lpc_set_psf(lpc_plan_t plan, const void* dev_psf, void* stream);
+int lpc_set_psf(lpc_plan_t plan, const void* dev_psf, void* stream);  /* [B,D,h,w,C] with LPC_FLAG_PSF_PER_SAMPLE */
 
 /* ADMM hyper-parameters (admm.py:39-42); recomputes R_divmat / X_divmat. */
 int lpc_set_admm_params(lpc_plan_t plan, double mu1, double mu2, double mu3, double tau,
@@ -169,6 +179,22 @@ int lpc_get_alpha(lpc_plan_t plan, void* dev_out, void* stream);
  * (stride 0 broadcasts a size-1 depth or channel axis, test_convolver.py:32-59). */
 int lpc_convolve(lpc_plan_t plan, const void* dev_in, const int64_t* in_strides, void* dev_out,
                  int adjoint, int pad, void* stream);
+
+/* ReconstructionAlgorithm.reconstruction_error (recon.py:607-653) on an LPC_ALGO_CONV plan built with the solver's
+ * convolver parameters: Hx = crop(convolve(pad(prediction))); normalize != 0: Hx = (Hx - min)/max(Hx - min) per
+ * (batch, depth) over (h,w,C) (recon.py:640-644); dev_out[b] = sum_{D,h,w,C} (Hx - lensless)^2 / npix, T[B].
+ * dev_prediction [B,D,h,w,C] and dev_lensless [B,Dl,h,w,C] (Dl in {1,D}) contiguous.  npix = prod(psf.shape)
+ * (recon.py:251: self._npix). */
+int lpc_reconstruction_error(lpc_plan_t plan, const void* dev_prediction, const void* dev_lensless, int Dl,
+                             int normalize, double npix, void* dev_out, void* stream);
+
+/* ReconstructionAlgorithm.set_image_estimate (recon.py:415-442): overwrite the current iterate only.  GD family:
+ * momentum / t_k / previous iterate are kept.  ADMM: a warm start (duals zeroed) -- documented deviation.
+ * dev_est as in lpc_reset. */
+int lpc_set_image_estimate(lpc_plan_t plan, const void* dev_est, void* stream);
+
+/* plan-level switches, see LPC_OPT_* */
+int lpc_set_option(lpc_plan_t plan, int option, double value);
 
 /* ---- introspection for the roofline ------------------ */
 /* algorithmic bytes per iteration for the whole plan (all B images):

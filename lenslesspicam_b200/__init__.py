@@ -3,37 +3,39 @@ lenslesspicam_b200 -- B200-native (sm_100a) iterative deconvolution engine behin
 the ``lensless.ADMM`` / ``lensless.FISTA`` / ``lensless.GradientDescent`` surface of
 LCAV/LenslessPiCam.  Python holds torch CUDA tensors; the arithmetic runs in
 ``liblpc.so`` (hand-written CUDA kernels + cuFFT) through the C-ABI of
-``include/lpc.h``.  There is no CPU fallback: importing the solver classes fails
-loudly if the extension has not been built.
+``include/lpc.h``.
+
+There is no CPU fallback: the first access to any solver / operator name (``from lenslesspicam_b200 import ADMM``)
+loads ``liblpc.so`` and raises if the extension has not been built.  Only ``lenslesspicam_b200.dist`` (torch.distributed
+plumbing: batch sharding, PSF broadcast, max-over-ranks timing) imports without the library, so the host-side
+multi-GPU logic can be exercised on machines that have neither a GPU nor the CUDA libraries.
 """
-from . import _lib
+import importlib
 
-_lib.load()  # raise now, not at first use, if liblpc.so is missing
+__version__ = "0.2.0"
 
-from .rfft_convolve import RealFFTConvolve2D  # noqa: E402
-from .recon import ReconstructionAlgorithm  # noqa: E402
-from .admm import ADMM, apply_admm  # noqa: E402
-from .gd import (  # noqa: E402
-    FISTA,
-    GradientDescent,
-    GradientDescentUpdate,
-    NesterovGradientDescent,
-    non_neg,
-)
+_EXPORTS = {
+    "RealFFTConvolve2D": "rfft_convolve",
+    "ReconstructionAlgorithm": "recon",
+    "ADMM": "admm", "apply_admm": "admm",
+    "FISTA": "gd", "GradientDescent": "gd", "GradientDescentUpdate": "gd", "NesterovGradientDescent": "gd",
+    "non_neg": "gd",
+    "UnrolledADMM": "unrolled", "UnrolledFISTA": "unrolled",
+}
+__all__ = sorted(_EXPORTS)
 
-from .unrolled import UnrolledADMM, UnrolledFISTA  # noqa: E402
 
-__version__ = "0.1.0"
-__all__ = [
-    "ADMM",
-    "FISTA",
-    "GradientDescent",
-    "GradientDescentUpdate",
-    "NesterovGradientDescent",
-    "RealFFTConvolve2D",
-    "UnrolledADMM",
-    "UnrolledFISTA",
-    "ReconstructionAlgorithm",
-    "apply_admm",
-    "non_neg",
-]
+def __getattr__(name):
+    mod = _EXPORTS.get(name)
+    if mod is None:
+        raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+    from . import _lib
+
+    _lib.load()  # raises ImportError when liblpc.so is missing: no CPU fallback
+    value = getattr(importlib.import_module(f".{mod}", __name__), name)
+    globals()[name] = value
+    return value
+
+
+def __dir__():
+    return sorted(list(globals()) + list(_EXPORTS))

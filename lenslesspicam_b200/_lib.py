@@ -20,7 +20,8 @@ ALGO_CONV, ALGO_ADMM, ALGO_GD, ALGO_NESTEROV, ALGO_FISTA = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 NORMS = {"backward": 0, "ortho": 1, "forward": 2}
 STATE_IMAGE_EST, STATE_FORWARD, STATE_XI, STATE_RHO, STATE_ETA0, STATE_ETA1 = range(6)
-FLAG_NONE, FLAG_NO_GRAPH, FLAG_ENGINE_V1 = 0, 1, 4
+FLAG_NONE, FLAG_NO_GRAPH, FLAG_ENGINE_V1, FLAG_PSF_PER_SAMPLE = 0, 1, 4, 8
+OPT_KEEP_X0, OPT_B2_PREFETCH = 1, 2
 
 _lock = threading.Lock()
 _lib = None
@@ -56,6 +57,9 @@ PROTOTYPES = {
     "lpc_get_H": (_i, [_vp, _vp, _vp]),
     "lpc_get_alpha": (_i, [_vp, _vp, _vp]),
     "lpc_convolve": (_i, [_vp, _vp, _i64p, _vp, _i, _i, _vp]),
+    "lpc_reconstruction_error": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
+    "lpc_set_image_estimate": (_i, [_vp, _vp, _vp]),
+    "lpc_set_option": (_i, [_vp, _i, _d]),
     "lpc_bytes_per_iter": (_i, [_vp, ctypes.POINTER(_d)]),
     "lpc_launches_per_iter": (_i, [_vp, _ip, _ip]),
     "lpc_profile": (_i, [_vp, _i, _vp, ctypes.POINTER(_d), _ip]),

@@ -19,6 +19,7 @@
 #include "lpc_fused_gd.cuh"
 #include "lpc_fused_tma.cuh"
 #include "lpc_gd.cuh"
+#include "lpc_metrics.cuh"
 #include "lpc_setup.cuh"
 #include "lpc_util.cuh"
 
@@ -27,6 +28,17 @@ using namespace lpc;
 namespace {
 
 thread_local std::string g_create_error;
+
+// Every entry point runs on the plan's device and RESTORES the caller's current device on return: torch reads its
+// current device from the CUDA runtime, so a bare cudaSetDevice here would silently re-target the caller's later work.
+struct DeviceGuard {
+    int prev = -1, dev;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
 
 int next_fast_len_impl(int n) {
     // smallest 2^a 3^b 5^c >= n  (scipy.fftpack.next_fast_len; rfft_convolve.py:16,112)
@@ -107,6 +119,10 @@ const ColsEntry* find_cols(int N) {
 struct lpc_plan_s {
     int device = 0, algo = 0, dtype = 0, norm = 0, B = 1, D = 1, C = 1, h = 0, w = 0, flags = 0;
     int Hp = 0, Wp = 0, sy = 0, sx = 0, Nh = 0, Np = 0, DC = 0;
+    int n_psf = 1;  // PSFs the plan holds: 1 (shared by every sample) or B (LPC_FLAG_PSF_PER_SAMPLE)
+    int PQ = 0;     // transfer-function planes = n_psf * D * C; plane p uses q = p % PQ
+    int NC = 0;     // columns of the per-PSF constants table = n_psf * C
+    int PS = 0;     // 1: per-sample constants (lpc_const_col)
     std::string err;
     virtual ~lpc_plan_s() {}
     virtual int init() = 0;
@@ -125,6 +141,9 @@ struct lpc_plan_s {
     virtual int get_H(void*, cudaStream_t) = 0;
     virtual int get_alpha(void*, cudaStream_t) = 0;
     virtual int convolve(const void*, const int64_t*, void*, int, int, cudaStream_t) = 0;
+    virtual int recon_error(const void*, const void*, int, int, double, void*, cudaStream_t) = 0;
+    virtual int set_image_estimate(const void*, cudaStream_t) = 0;
+    virtual int set_option(int, double) = 0;
     virtual int bytes_per_iter(double*) = 0;
     virtual int launches_per_iter(int*, int*) = 0;
     virtual int profile(int, cudaStream_t, double*, int*) = 0;
@@ -228,12 +247,20 @@ struct Plan : lpc_plan_s {
     int gd_it = 0;                                     // FISTA schedule position (iterations since reset)
     double lip = 1.8, nmu = 0.9, tk0 = 1.0, tk = 1.0;
     bool psf_set = false, data_set = false, state_ready = false, fista_first = true;
-    // ---- graph cache (one entry)
-    cudaGraphExec_t gexec = nullptr;
-    int g_niter = -1, g_eta = -1, g_first = -1, g_vh = -1, g_gdit = -1;
-    double g_pm[3] = {0, 0, 0};
-    double g_tk = 0;
-    cudaStream_t g_stream = nullptr;
+    bool keep_x0 = false;  // LPC_OPT_KEEP_X0: lpc_set_psf leaves the initial-value constants (psf min / max) alone
+    // ---- graph cache: a few captured iteration loops, least recently used evicted (an apply() that alternates
+    //      iteration counts -- disp_iter chunks, a warm-up run next to the real one -- replays instead of re-capturing)
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int niter = -1, eta = -1, first = -1, vh = -1, gdit = -1;
+        double pm[3] = {0, 0, 0};
+        double tk = 0;
+        cudaStream_t stream = nullptr;
+        uint64_t stamp = 0;
+    };
+    static constexpr int MAX_GRAPHS = 4;
+    std::vector<GraphEntry> graphs;
+    uint64_t graph_clock = 0;
 
     ~Plan() override {
         cudaSetDevice(device);
@@ -285,8 +312,8 @@ struct Plan : lpc_plan_s {
     }
 
     void drop_graph() {
-        if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
-        g_niter = -1;
+        for (GraphEntry& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
     }
 
     int make_fft(cufftHandle* hnd, bool* have, cufftType type, int batch) {
@@ -300,6 +327,7 @@ struct Plan : lpc_plan_s {
         return LPC_OK;
     }
     int bind_work() {
+        drop_graph();  // captured cuFFT nodes carry the old work-area pointer
         if (work) { cudaFree(work); work = nullptr; }
         if (work_bytes) {
             cudaError_t e = cudaMalloc(&work, work_bytes);
@@ -321,6 +349,10 @@ struct Plan : lpc_plan_s {
         Nh = Wp / 2 + 1;
         Np = B * D * C;
         DC = D * C;
+        PS = (flags & LPC_FLAG_PSF_PER_SAMPLE) ? 1 : 0;
+        n_psf = PS ? B : 1;
+        PQ = n_psf * DC;
+        NC = n_psf * C;
         plane = (int64_t)Hp * Wp;
         splane = (int64_t)Hp * Nh;
         vec_ok = (Wp % VEC) == 0;
@@ -332,11 +364,11 @@ struct Plan : lpc_plan_s {
             dpitch = w;
         }
         int rc;
-        if ((rc = alloc(&psfpad, (size_t)DC * plane))) return rc;
-        if ((rc = alloc(&Hc, (size_t)DC * splane))) return rc;
+        if ((rc = alloc(&psfpad, (size_t)PQ * plane))) return rc;
+        if ((rc = alloc(&Hc, (size_t)PQ * splane))) return rc;
         if ((rc = alloc(&Sy, (size_t)Hp))) return rc;
         if ((rc = alloc(&Sx, (size_t)Nh))) return rc;
-        if ((rc = alloc(&consts, (size_t)4 * C))) return rc;
+        if ((rc = alloc(&consts, (size_t)4 * NC))) return rc;
         if ((rc = alloc(&data, (size_t)Np * h * dpitch))) return rc;  // sized for Dd == D
         int nb = Np;
         if (algo == LPC_ALGO_ADMM && !(flags & LPC_FLAG_ENGINE_V1) && getenv("LPC_ENGINE_V1") == nullptr) {
@@ -349,7 +381,7 @@ struct Plan : lpc_plan_s {
             if ((rc = alloc(&rho, (size_t)Np * plane))) return rc;
             if ((rc = alloc(&eta[0], (size_t)2 * Np * plane))) return rc;
             if ((rc = alloc(&eta[1], (size_t)2 * Np * plane))) return rc;
-            if ((rc = alloc(&Rn, (size_t)DC * splane))) return rc;
+            if ((rc = alloc(&Rn, (size_t)PQ * splane))) return rc;
         } else {
             if (algo >= LPC_ALGO_GD && !(flags & LPC_FLAG_ENGINE_V1) && getenv("LPC_ENGINE_V1") == nullptr) {
                 if ((rc = init_gd2())) return rc;
@@ -369,7 +401,7 @@ struct Plan : lpc_plan_s {
             }
         }
         if (nb > 0 && (rc = alloc(&spec, (size_t)nb * splane))) return rc;
-        if ((rc = make_fft(&fwd_psf, &have_fwd_psf, FftTraits<T>::R2C, DC))) return rc;
+        if ((rc = make_fft(&fwd_psf, &have_fwd_psf, FftTraits<T>::R2C, PQ))) return rc;
         if (nb > 0) {
             if ((rc = make_fft(&fwd, &have_fwd, FftTraits<T>::R2C, nb))) return rc;
             if ((rc = make_fft(&inv, &have_inv, FftTraits<T>::C2R, nb))) return rc;
@@ -516,13 +548,13 @@ struct Plan : lpc_plan_s {
             if (const char* e = getenv("LPC_COLS_VARIANT")) cols_variant = atoi(e) ? 1 : 0;
 
             fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;
-            fk.n_planes = Np; fk.DC = DC;
+            fk.n_planes = Np; fk.DC = PQ;
             int rc;
             const size_t tsz = (size_t)Np * fk.NT * Hp * 2 * LPC_NCT;
             if ((rc = alloc(&Tin, tsz))) return rc;
             if ((rc = alloc(&Tout, tsz))) return rc;
-            if ((rc = alloc(&Ht, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
-            if ((rc = alloc(&Rt, (size_t)DC * fk.NT * Hp * LPC_NCT))) return rc;
+            if ((rc = alloc(&Ht, (size_t)PQ * fk.NT * Hp * LPC_NCT))) return rc;
+            if ((rc = alloc(&Rt, (size_t)PQ * fk.NT * Hp * LPC_NCT))) return rc;
             if ((rc = upload_twiddles())) return rc;
             if ((rc = init_cols_tma(max_optin))) return rc;
             v2 = true;
@@ -573,7 +605,7 @@ struct Plan : lpc_plan_s {
             for (int kx = 0; kx < NT * LPC_NCT; ++kx) gx[kx] = (T)(2.0 - 2.0 * std::cos(2.0 * M_PI * (double)(kx % Wp) / (double)Wp));
             if ((rc = alloc(&Gx, gx.size()))) return rc;
             LPC_CK(cudaMemcpy(Gx, gx.data(), gx.size() * sizeof(T), cudaMemcpyHostToDevice));
-            if ((rc = alloc(&Hm, (size_t)DC * NT * Hp * LPC_NCT))) return rc;
+            if ((rc = alloc(&Hm, (size_t)PQ * NT * Hp * LPC_NCT))) return rc;
             cols_tma = want;
             return LPC_OK;
         }
@@ -600,7 +632,7 @@ struct Plan : lpc_plan_s {
             LPC_CK(cudaMemcpy(tabs_ip, tabs.data(), tabs.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
             if ((rc = alloc(&kymap, (size_t)Hp))) return rc;
             LPC_CK(cudaMemcpy(kymap, km.data(), (size_t)Hp * sizeof(int), cudaMemcpyHostToDevice));
-            if ((rc = alloc(&Fgm, (size_t)2 * DC * gk.NTg * Hp * LPC_GNC))) return rc;
+            if ((rc = alloc(&Fgm, (size_t)2 * PQ * gk.NTg * Hp * LPC_GNC))) return rc;
             gd_tma = 1;
             return LPC_OK;
         }
@@ -626,10 +658,10 @@ struct Plan : lpc_plan_s {
             LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->gd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
             gk.Hp = Hp; gk.Wp = Wp; gk.Nh = Nh; gk.NTg = (Nh + LPC_GNC - 1) / LPC_GNC;
             gk.h = h; gk.w = w; gk.sy = sy; gk.sx = sx;
-            gk.n_planes = Np; gk.DC = DC; gk.C = C; gk.D = D; gk.Dd = Dd;
+            gk.n_planes = Np; gk.DC = PQ; gk.C = C; gk.D = D; gk.Dd = Dd; gk.NC = NC; gk.PS = PS;
             int rc;
             if ((rc = alloc(&Tg, (size_t)Np * gk.NTg * h * LPC_GNC))) return rc;
-            if ((rc = alloc(&Fg, (size_t)2 * DC * gk.NTg * Hp * LPC_GNC))) return rc;
+            if ((rc = alloc(&Fg, (size_t)2 * PQ * gk.NTg * Hp * LPC_GNC))) return rc;
             if ((rc = upload_twiddles())) return rc;
             if ((rc = init_gd_tma(max_optin))) return rc;
             gd2 = true;
@@ -653,13 +685,13 @@ struct Plan : lpc_plan_s {
             dim3 grid(gk.NTg, np);
             GdFusedK k = gk; k.plane0 = p0;
             if (gd_tma) {
-                const Cplx* Fm_ = Fgm + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
+                const Cplx* Fm_ = Fgm + (adjoint ? (int64_t)PQ * gk.NTg * Hp * LPC_GNC : 0);
                 const int n_items = gk.NTg * np;
                 cols_entry->gd_tma<<<n_items < n_sms ? n_items : n_sms, LPC_TMA_NG * LPC_TMA_NTHG + 32, smem_gd_tma, st>>>(k, n_items, tabs_ip, Tg, Fm_);
                 LPC_KCHECK();
                 return LPC_OK;
             }
-            const Cplx* F = Fg + (adjoint ? (int64_t)DC * gk.NTg * Hp * LPC_GNC : 0);
+            const Cplx* F = Fg + (adjoint ? (int64_t)PQ * gk.NTg * Hp * LPC_GNC : 0);
             cols_entry->gd<<<grid, 576, smem_col, st>>>(k, tw_col, tw_col_rev, Tg, F);
             LPC_KCHECK();
         }
@@ -674,7 +706,7 @@ struct Plan : lpc_plan_s {
             const int i = gd_it < n_sched ? gd_it : n_sched - 1;
             f.beta = (T)((s_tk[i] - 1.0) / s_tk[i + 1]);
             f.first = 0;
-            f.consts = alpha_sched + (size_t)i * 4 * C;
+            f.consts = alpha_sched + (size_t)i * 4 * NC;
             ++gd_it;
         } else {
             const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;  // gd.py:238
@@ -711,11 +743,11 @@ struct Plan : lpc_plan_s {
     }
 
     int tile_HR(cudaStream_t st) {
-        k_tile_HR<T><<<1184, 256, 0, st>>>(Hc, Rn, Ht, Rt, DC, Hp, Nh, fk.NT);
+        k_tile_HR<T><<<1184, 256, 0, st>>>(Hc, Rn, Ht, Rt, PQ, Hp, Nh, fk.NT);
         LPC_KCHECK();
         if constexpr (std::is_same<T, float>::value) {
             if (cols_tma) {
-                k_tile_H_mid<T><<<1184, 256, 0, st>>>(Hc, kymap, Hm, DC, Hp, Nh, fk.NT, cols_entry->radix[cols_entry->npass - 1]);
+                k_tile_H_mid<T><<<1184, 256, 0, st>>>(Hc, kymap, Hm, PQ, Hp, Nh, fk.NT, cols_entry->radix[cols_entry->npass - 1]);
                 LPC_KCHECK();
             }
         }
@@ -784,7 +816,7 @@ struct Plan : lpc_plan_s {
         GdK k;
         k.Hp = Hp; k.Wp = Wp; k.Nh = Nh; k.h = h; k.w = w; k.sy = sy; k.sx = sx;
         k.C = C; k.D = D; k.Dd = Dd; k.dpitch = dpitch; k.plane = plane; k.dplane = (int64_t)h * dpitch;
-        k.n_planes = Np;
+        k.n_planes = Np; k.NC = NC; k.PS = PS;
         return k;
     }
 
@@ -792,13 +824,13 @@ struct Plan : lpc_plan_s {
     int compute_R(cudaStream_t st, int it = 0) {
         double m[4];
         admm_params(it, m);
-        k_admm_R<T><<<1184, 256, 0, st>>>(Hc, Rn, DC, Hp, Wp, Nh, m[0], m[1], m[2]);
+        k_admm_R<T><<<1184, 256, 0, st>>>(Hc, Rn, PQ, Hp, Wp, Nh, m[0], m[1], m[2]);
         LPC_KCHECK();
         if (v2) return tile_HR(st);
         return LPC_OK;
     }
     int compute_alpha(cudaStream_t st) {
-        k_alpha<T><<<1, 32, 0, st>>>(consts, C, (T)lip);
+        k_alpha<T><<<(NC + 127) / 128, 128, 0, st>>>(consts, NC, (T)lip);
         LPC_KCHECK();
         return LPC_OK;
     }
@@ -811,33 +843,35 @@ struct Plan : lpc_plan_s {
         const T* psf = (const T*)dev_psf;
         int rc;
         // pad (rfft_convolve.py:84-100) -> rfft2 (rfft_convolve.py:121-123)
-        if ((rc = pack(psf, contiguous(D, h, w, C), nullptr, Strides5{}, psfpad, 1, D, h, w, plane, Wp, sy, sx, st))) return rc;
+        if ((rc = pack(psf, contiguous(D, h, w, C), nullptr, Strides5{}, psfpad, n_psf, D, h, w, plane, Wp, sy, sx, st))) return rc;
         LPC_CF(cufftSetStream(fwd_psf, st));
         LPC_CF(FftTraits<T>::fwd(fwd_psf, psfpad, Hc));
         if (norm != LPC_NORM_BACKWARD) {
             const double n = (double)Hp * (double)Wp;
             const T scale = (T)(norm == LPC_NORM_ORTHO ? 1.0 / std::sqrt(n) : 1.0 / n);
-            k_scale_complex<T><<<1184, 256, 0, st>>>(Hc, (int64_t)DC * splane, scale);
+            k_scale_complex<T><<<1184, 256, 0, st>>>(Hc, (int64_t)PQ * splane, scale);
             LPC_KCHECK();
         }
         // constants derived from H / PSF
-        k_init_consts<T><<<1, 32, 0, st>>>(consts, psf, C);
+        k_init_consts<T><<<(NC + 127) / 128, 128, 0, st>>>(consts, psf, C, NC, (int64_t)D * h * w * C, keep_x0 ? 1 : 0);
         LPC_KCHECK();
         {
-            dim3 g(64, DC);
-            k_hh_max<T><<<g, 256, 0, st>>>(Hc, consts, C, splane);
-            dim3 g2(64, C);
-            k_psf_minmax<T><<<g2, 256, 0, st>>>(psf, (int64_t)D * h * w, C, consts + C, consts + 2 * C);
+            dim3 g(64, PQ);
+            k_hh_max<T><<<g, 256, 0, st>>>(Hc, consts, C, DC, PS, splane);
+            if (!keep_x0) {
+                dim3 g2(64, C, n_psf);
+                k_psf_minmax<T><<<g2, 256, 0, st>>>(psf, (int64_t)D * h * w, C, consts + NC, consts + 2 * NC);
+            }
             LPC_KCHECK();
         }
         if ((rc = compute_alpha(st))) return rc;
         if (algo == LPC_ALGO_ADMM && (rc = compute_R(st))) return rc;
         if (gd2) {
-            k_gd_tile_filter<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, Fg, DC, Hp, Wp, Nh, gk.NTg);
+            k_gd_tile_filter<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, Fg, PQ, Hp, Wp, Nh, gk.NTg);
             LPC_KCHECK();
             if constexpr (std::is_same<T, float>::value) {
                 if (gd_tma) {
-                    k_gd_tile_filter_mid<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, kymap, Fgm, DC, Hp, Wp, Nh, gk.NTg,
+                    k_gd_tile_filter_mid<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, kymap, Fgm, PQ, Hp, Wp, Nh, gk.NTg,
                                                                  cols_entry->radix[cols_entry->npass - 1]);
                     LPC_KCHECK();
                 }
@@ -888,9 +922,9 @@ struct Plan : lpc_plan_s {
         n_sched = 0;
         state_ready = false;  // the previous-iterate convention differs: reset before the next run
         if (n == 0) return LPC_OK;
-        std::vector<T> tab((size_t)n * 4 * C, T(0));
+        std::vector<T> tab((size_t)n * 4 * NC, T(0));  // one constants table per iteration; the steps are shared by all PSFs
         for (int i = 0; i < n; ++i)
-            for (int c = 0; c < C; ++c) tab[(size_t)i * 4 * C + 3 * C + c] = (T)alpha[(size_t)i * C + c];
+            for (int j = 0; j < NC; ++j) tab[(size_t)i * 4 * NC + 3 * NC + j] = (T)alpha[(size_t)i * C + j % C];
         if (tab.size() > alpha_cap) {  // (an outgrown table is released with the plan)
             int rc = alloc(&alpha_sched, tab.size());
             if (rc) return rc;
@@ -955,7 +989,7 @@ struct Plan : lpc_plan_s {
     int spec_mul(Cplx* s, int nplanes, int adjoint, cudaStream_t st) {
         dim3 grid((unsigned)((splane + 255) / 256), nplanes);
         const T scale = (T)(1.0 / ((double)Hp * (double)Wp));
-        k_spec_mul<T><<<grid, 256, 0, st>>>(s, Hc, Sy, Sx, DC, Hp, Nh, adjoint, scale);
+        k_spec_mul<T><<<grid, 256, 0, st>>>(s, Hc, Sy, Sx, PQ, Hp, Nh, adjoint, scale);
         LPC_KCHECK();
         return LPC_OK;
     }
@@ -1012,7 +1046,7 @@ struct Plan : lpc_plan_s {
                                xoy, xox, st))) return rc;
             } else {
                 dim3 grid((w + 127) / 128, h, Np);
-                k_fill_x0<T><<<grid, 128, 0, st>>>(xdst, consts, C, h, w, xps, xpitch, xoy, xox);
+                k_fill_x0<T><<<grid, 128, 0, st>>>(xdst, consts, C, DC, NC, PS, h, w, xps, xpitch, xoy, xox);
                 LPC_KCHECK();
             }
             if (gd2 && (rc = gd2_rows(LPC_GD_INIT, T(0), 0, st))) return rc;  // row spectra of the initial estimate
@@ -1076,7 +1110,7 @@ struct Plan : lpc_plan_s {
         LPC_CF(FftTraits<T>::fwd(fwd, AX, spec));
         LPC_EV(2);
         dim3 grid((unsigned)((splane + 255) / 256), Np);
-        k_admm_spectral<T><<<grid, 256, 0, st>>>(spec, Hc, Rn, Sy, Sx, Np, DC, Hp, Nh);
+        k_admm_spectral<T><<<grid, 256, 0, st>>>(spec, Hc, Rn, Sy, Sx, Np, PQ, Hp, Nh);
         LPC_KCHECK();
         LPC_EV(3);
         LPC_CF(FftTraits<T>::inv(inv, spec, VH));
@@ -1255,11 +1289,19 @@ struct Plan : lpc_plan_s {
 
         const int first = fista_first ? 1 : 0;
         const int vh0 = vh_valid ? 1 : 0;  // the first captured iteration skips B1 when VH already holds V, HV
-        const bool hit = gexec && g_niter == n_iter && g_eta == eta_cur && g_stream == st && g_vh == vh0 &&
-                         (algo != LPC_ALGO_FISTA || (g_tk == tk && g_first == first && g_gdit == gd_it)) &&
-                         (algo != LPC_ALGO_ADMM || (g_pm[0] == pm1 && g_pm[1] == pm2 && g_pm[2] == pm3));
+        GraphEntry* hit = nullptr;
+        for (GraphEntry& g : graphs) {
+            if (g.exec && g.niter == n_iter && g.eta == eta_cur && g.stream == st && g.vh == vh0 &&
+                (algo != LPC_ALGO_FISTA || (g.tk == tk && g.first == first && g.gdit == gd_it)) &&
+                (algo != LPC_ALGO_ADMM || (g.pm[0] == pm1 && g.pm[1] == pm2 && g.pm[2] == pm3))) { hit = &g; break; }
+        }
         if (!hit) {
-            drop_graph();
+            if ((int)graphs.size() >= MAX_GRAPHS) {  // evict the least recently used entry
+                size_t lru = 0;
+                for (size_t i = 1; i < graphs.size(); ++i) if (graphs[i].stamp < graphs[lru].stamp) lru = i;
+                if (graphs[lru].exec) cudaGraphExecDestroy(graphs[lru].exec);
+                graphs.erase(graphs.begin() + lru);
+            }
             const int eta0 = eta_cur, gdit0 = gd_it;
             const double tk_start = tk, pm0[3] = {pm1, pm2, pm3};
             cudaGraph_t graph = nullptr;
@@ -1268,11 +1310,14 @@ struct Plan : lpc_plan_s {
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             if (rc != LPC_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
             if (e != cudaSuccess) return fail(LPC_ECUDA, "cudaStreamEndCapture", cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&gexec, graph, 0);
+            GraphEntry g;
+            e = cudaGraphInstantiate(&g.exec, graph, 0);
             cudaGraphDestroy(graph);
-            if (e != cudaSuccess) { gexec = nullptr; return fail(LPC_ECUDA, "cudaGraphInstantiate", cudaGetErrorString(e)); }
-            g_niter = n_iter; g_eta = eta0; g_tk = tk_start; g_first = first; g_stream = st; g_vh = vh0;
-            g_gdit = gdit0; g_pm[0] = pm0[0]; g_pm[1] = pm0[1]; g_pm[2] = pm0[2];
+            if (e != cudaSuccess) return fail(LPC_ECUDA, "cudaGraphInstantiate", cudaGetErrorString(e));
+            g.niter = n_iter; g.eta = eta0; g.tk = tk_start; g.first = first; g.stream = st; g.vh = vh0;
+            g.gdit = gdit0; g.pm[0] = pm0[0]; g.pm[1] = pm0[1]; g.pm[2] = pm0[2];
+            graphs.push_back(g);
+            hit = &graphs.back();
             // iterate() advanced the host-side bookkeeping while capturing; nothing ran yet
         } else {
             // replay: advance the host-side bookkeeping exactly as iterate() would
@@ -1283,7 +1328,8 @@ struct Plan : lpc_plan_s {
                 fista_first = false;
             }
         }
-        LPC_CK(cudaGraphLaunch(gexec, st));
+        hit->stamp = ++graph_clock;
+        LPC_CK(cudaGraphLaunch(hit->exec, st));
         vh_valid = false;  // V / HV in VH are stale as soon as an iteration has run (engine v2 keeps only spectra)
         return LPC_OK;
     }
@@ -1335,14 +1381,14 @@ struct Plan : lpc_plan_s {
     int get_H(void* dev_out, cudaStream_t st) override {
         if (!psf_set) return fail(LPC_ESTATE, "get_H", "PSF not set");
         LPC_CK(cudaSetDevice(device));
-        k_unpack_complex<T><<<1184, 256, 0, st>>>(Hc, (Cplx*)dev_out, D, C, Hp, Nh);
+        k_unpack_complex<T><<<1184, 256, 0, st>>>(Hc, (Cplx*)dev_out, n_psf * D, C, Hp, Nh);
         LPC_KCHECK();
         return LPC_OK;
     }
     int get_alpha(void* dev_out, cudaStream_t st) override {
         if (!psf_set) return fail(LPC_ESTATE, "get_alpha", "PSF not set");
         LPC_CK(cudaSetDevice(device));
-        LPC_CK(cudaMemcpyAsync(dev_out, consts + 3 * C, C * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        LPC_CK(cudaMemcpyAsync(dev_out, consts + 3 * NC, NC * sizeof(T), cudaMemcpyDeviceToDevice, st));
         return LPC_OK;
     }
 
@@ -1368,6 +1414,84 @@ struct Plan : lpc_plan_s {
         if ((rc = spec_mul(spec, Np, adjoint, st))) return rc;
         LPC_CF(FftTraits<T>::inv(inv, spec, rpad));
         return unpack(rpad, plane, Wp, oy, ox, (T*)dev_out, B * D, hh, ww, 0, st);
+    }
+
+    // reconstruction_error (recon.py:607-653): convolve the prediction (ALWAYS through pad -> convolve -> crop: with
+    // pad=False the reference pads the prediction itself and crops the result, :633-638), then min/max-normalise
+    // per (batch, depth) and reduce the squared error against the measurement per batch entry.  dev_out: T[B].
+    T* err_mm = nullptr;
+    double* err_acc = nullptr;
+    int recon_error(const void* dev_pred, const void* dev_lensless, int Dl, int normalize, double npix, void* dev_out,
+                    cudaStream_t st) override {
+        if (algo != LPC_ALGO_CONV) return fail(LPC_ESTATE, "reconstruction_error", "not a convolver plan");
+        if (!psf_set) return fail(LPC_ESTATE, "reconstruction_error", "PSF not set");
+        if (!dev_pred || !dev_lensless || !dev_out) return fail(LPC_EINVAL, "reconstruction_error", "null pointer");
+        if (Dl != 1 && Dl != D) return fail(LPC_EINVAL, "reconstruction_error", "measurement depth must be 1 or the PSF depth");
+        if (!(npix > 0)) return fail(LPC_EINVAL, "reconstruction_error", "npix must be > 0");
+        int rc;
+        if (!err_mm) {
+            if ((rc = alloc(&err_mm, (size_t)2 * B * D))) return rc;
+            if ((rc = alloc(&err_acc, (size_t)B))) return rc;
+        }
+        if (xpad_border_dirty) {
+            LPC_CK(cudaMemsetAsync(xpad, 0, (size_t)Np * plane * sizeof(T), st));
+            xpad_border_dirty = false;
+        }
+        if ((rc = pack((const T*)dev_pred, contiguous(D, h, w, C), nullptr, Strides5{}, xpad, B, D, h, w, plane, Wp, sy, sx, st))) return rc;
+        LPC_CF(cufftSetStream(fwd, st));
+        LPC_CF(cufftSetStream(inv, st));
+        LPC_CF(FftTraits<T>::fwd(fwd, xpad, spec));
+        if ((rc = spec_mul(spec, Np, 0, st))) return rc;
+        LPC_CF(FftTraits<T>::inv(inv, spec, rpad));
+        const int G = B * D;
+        k_err_init<T><<<(G + B + 127) / 128, 128, 0, st>>>(err_mm, G, err_acc, B);
+        dim3 grid(64, G);
+        if (normalize) k_err_minmax<T><<<grid, 256, 0, st>>>(rpad, plane, Wp, sy, sx, C, h, w, err_mm);
+        k_err_sse<T><<<grid, 256, 0, st>>>(rpad, plane, Wp, sy, sx, C, D, Dl, h, w, err_mm, normalize, (const T*)dev_lensless, err_acc);
+        k_err_final<T><<<(B + 127) / 128, 128, 0, st>>>(err_acc, (T*)dev_out, B, 1.0 / npix);
+        LPC_KCHECK();
+        return LPC_OK;
+    }
+
+    // set_image_estimate (recon.py:415-442): overwrite the current iterate, leave everything else alone.
+    // GD family: x <- est; Nesterov's p, FISTA's t_k and previous iterate stay.  Right after a reset FISTA's
+    // previous iterate ALIASES the estimate (gd.py:233); assigning a new tensor breaks the alias, so the old
+    // estimate is what the next update's momentum term sees.
+    // ADMM: implemented as a warm start (V <- est, HV, Psi V recomputed, duals zeroed) -- DEVIATION: the reference
+    // keeps its duals and, for one iteration, the stale HV / Psi V of the previous iterate.
+    int set_image_estimate(const void* dev_est, cudaStream_t st) override {
+        if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "set_image_estimate", "convolver plans have no solver state");
+        if (!dev_est) return fail(LPC_EINVAL, "set_image_estimate", "null estimate");
+        if (algo == LPC_ALGO_ADMM || !state_ready) return reset(dev_est, st);
+        int rc;
+        T* xdst = gd2 ? xu : xpad;
+        if (algo == LPC_ALGO_FISTA && fista_first && n_sched == 0) {
+            if (gd2) LPC_CK(cudaMemcpyAsync(mom, xu, (size_t)Np * h * w * sizeof(T), cudaMemcpyDeviceToDevice, st));
+            else if ((rc = copy_window(xpad, mom, st))) return rc;
+            fista_first = false;
+        }
+        const int64_t xps = gd2 ? (int64_t)h * w : plane;
+        const int xpitch = gd2 ? w : Wp, xoy = gd2 ? 0 : sy, xox = gd2 ? 0 : sx;
+        if ((rc = pack((const T*)dev_est, contiguous(D, h, w, C), nullptr, Strides5{}, xdst, B, D, h, w, xps, xpitch, xoy, xox, st))) return rc;
+        if (gd2 && (rc = gd2_rows(LPC_GD_INIT, T(0), 0, st))) return rc;  // row spectra of the new estimate
+        return LPC_OK;
+    }
+    // window of padded planar planes -> unpadded planar [Np][h][w]
+    int copy_window(const T* src, T* dst, cudaStream_t st) {
+        LPC_CK(cudaMemcpy2DAsync(dst, (size_t)w * sizeof(T), src + (int64_t)sy * Wp + sx, (size_t)Wp * sizeof(T), (size_t)w * sizeof(T), (size_t)h,
+                                 cudaMemcpyDeviceToDevice, st));
+        for (int p = 1; p < Np; ++p)
+            LPC_CK(cudaMemcpy2DAsync(dst + (int64_t)p * h * w, (size_t)w * sizeof(T), src + (int64_t)p * plane + (int64_t)sy * Wp + sx,
+                                     (size_t)Wp * sizeof(T), (size_t)w * sizeof(T), (size_t)h, cudaMemcpyDeviceToDevice, st));
+        return LPC_OK;
+    }
+
+    int set_option(int option, double value) override {
+        switch (option) {
+            case LPC_OPT_KEEP_X0: keep_x0 = value != 0.0; return LPC_OK;
+            case LPC_OPT_B2_PREFETCH: b2_prefetch = (int)value; drop_graph(); return LPC_OK;
+            default: return fail(LPC_EINVAL, "set_option", "unknown option");
+        }
     }
 
     // ---------------------------------------------------------------- introspection
@@ -1457,6 +1581,7 @@ int lpc_plan_create(lpc_plan_t* out, int device, int algo, int dtype, int norm, 
     if (!p) return bad(LPC_ENOMEM, "host allocation failed");
     p->device = device; p->algo = algo; p->dtype = dtype; p->norm = norm;
     p->B = B; p->D = D; p->C = C; p->h = h; p->w = w; p->flags = flags;
+    DeviceGuard guard(device);
     int rc = p->init();
     if (rc != LPC_OK) {
         g_create_error = p->err;
@@ -1468,12 +1593,15 @@ int lpc_plan_create(lpc_plan_t* out, int device, int algo, int dtype, int norm, 
 }
 
 int lpc_plan_destroy(lpc_plan_t plan) {
+    if (!plan) return LPC_OK;
+    DeviceGuard guard(plan->device);
     delete plan;
     return LPC_OK;
 }
 
-#define LPC_NEED(plan) \
-    if (!(plan)) return LPC_EINVAL
+#define LPC_NEED(plan)                \
+    if (!(plan)) return LPC_EINVAL;   \
+    DeviceGuard lpc_guard_((plan)->device)
 
 int lpc_set_psf(lpc_plan_t plan, const void* dev_psf, void* stream) {
     LPC_NEED(plan);
@@ -1537,6 +1665,19 @@ int lpc_convolve(lpc_plan_t plan, const void* dev_in, const int64_t* in_strides,
                  void* stream) {
     LPC_NEED(plan);
     return plan->convolve(dev_in, in_strides, dev_out, adjoint, pad, (cudaStream_t)stream);
+}
+int lpc_reconstruction_error(lpc_plan_t plan, const void* dev_prediction, const void* dev_lensless, int Dl, int normalize,
+                             double npix, void* dev_out, void* stream) {
+    LPC_NEED(plan);
+    return plan->recon_error(dev_prediction, dev_lensless, Dl, normalize, npix, dev_out, (cudaStream_t)stream);
+}
+int lpc_set_image_estimate(lpc_plan_t plan, const void* dev_est, void* stream) {
+    LPC_NEED(plan);
+    return plan->set_image_estimate(dev_est, (cudaStream_t)stream);
+}
+int lpc_set_option(lpc_plan_t plan, int option, double value) {
+    LPC_NEED(plan);
+    return plan->set_option(option, value);
 }
 int lpc_bytes_per_iter(lpc_plan_t plan, double* algorithmic_bytes) {
     LPC_NEED(plan);

@@ -26,6 +26,7 @@
 #pragma once
 #include "lpc_fft.cuh"
 #include "lpc_fused.cuh"
+#include "lpc_setup.cuh"
 #include "lpc_util.cuh"
 
 namespace lpc {
@@ -35,8 +36,9 @@ constexpr int LPC_GNC = 4;  // columns per tile of the G-layout
 struct GdFusedK {
     int Hp, Wp, Nh, NTg;
     int h, w, sy, sx;
-    int n_planes, DC, C, D, Dd;
+    int n_planes, DC, C, D, Dd;   // DC = number of transfer-function planes (D*C, or B*D*C with one PSF per sample)
     int plane0;  // first plane of this launch
+    int NC, PS;  // columns of the constants table, 1 = one PSF per sample (lpc_const_col, lpc_setup.cuh)
 };
 
 enum { LPC_GD_INIT = 0, LPC_GD_RESID = 1, LPC_GD_UPD_GD = 2, LPC_GD_UPD_NESTEROV = 3, LPC_GD_UPD_FISTA = 4 };
@@ -113,7 +115,7 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
 
     // ---- last inverse pass -> element-wise stage -> first forward pass, in registers
     const int64_t ia = ((int64_t)p * h + ra) * w, ib = ia + w;
-    const T alpha = (MODE >= LPC_GD_UPD_GD) ? consts[3 * f.C + p % f.C] : T(0);
+    const T alpha = (MODE >= LPC_GD_UPD_GD) ? consts[3 * f.NC + lpc_const_col(p, f.D * f.C, f.C, f.PS)] : T(0);
     const T* dpl = data + (int64_t)gdf_data_plane(p, f) * h * w;
     constexpr int MAXB = (NSL + NTH - 1) / NTH;
     C v[MAXB][RL];

@@ -9,6 +9,7 @@
 // writes the new estimate straight back into the window.  Likewise the residual
 // crop(Hx) - y is written into the window of a second zero-bordered buffer (dpad).
 #pragma once
+#include "lpc_setup.cuh"
 #include "lpc_util.cuh"
 
 namespace lpc {
@@ -21,6 +22,7 @@ struct GdK {
     int64_t plane;     // Hp*Wp
     int64_t dplane;    // h*dpitch
     int n_planes;
+    int NC, PS;        // columns of the constants table, 1 = one PSF per sample (lpc_const_col, lpc_setup.cuh)
 };
 
 __device__ __forceinline__ int gd_data_plane(int p, const GdK& k) {
@@ -83,7 +85,7 @@ k_gd_update(GdK k, const T* __restrict__ grad, const T* __restrict__ consts, T* 
     if (x >= k.w) return;
     const int p = blockIdx.z;
     const int64_t o = (int64_t)p * k.plane + (int64_t)(blockIdx.y + k.sy) * k.Wp + (x + k.sx);
-    const T alpha = consts[3 * k.C + p % k.C];
+    const T alpha = consts[3 * k.NC + lpc_const_col(p, k.D * k.C, k.C, k.PS)];
     T v = xpad[o] - alpha * grad[o];
     xpad[o] = v > T(0) ? v : T(0);
 }
@@ -100,7 +102,7 @@ k_nesterov_update(GdK k, const T* __restrict__ grad, const T* __restrict__ const
     const int p = blockIdx.z;
     const int64_t o = (int64_t)p * k.plane + (int64_t)(blockIdx.y + k.sy) * k.Wp + (x + k.sx);
     const int64_t m = ((int64_t)p * k.h + blockIdx.y) * k.w + x;
-    const T alpha = consts[3 * k.C + p % k.C];
+    const T alpha = consts[3 * k.NC + lpc_const_col(p, k.D * k.C, k.C, k.PS)];
     const T p_prev = mom[m];
     const T p_new = mu * p_prev - alpha * grad[o];
     mom[m] = p_new;
@@ -123,7 +125,7 @@ k_fista_update(GdK k, const T* __restrict__ grad, const T* __restrict__ consts, 
     const int p = blockIdx.z;
     const int64_t o = (int64_t)p * k.plane + (int64_t)(blockIdx.y + k.sy) * k.Wp + (x + k.sx);
     const int64_t m = ((int64_t)p * k.h + blockIdx.y) * k.w + x;
-    const T alpha = consts[3 * k.C + p % k.C];
+    const T alpha = consts[3 * k.NC + lpc_const_col(p, k.D * k.C, k.C, k.PS)];
     const T z = xpad[o] - alpha * grad[o];
     const T xk = z > T(0) ? z : T(0);
     const T prev = first ? z : xk_prev[m];

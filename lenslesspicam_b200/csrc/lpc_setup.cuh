@@ -123,13 +123,21 @@ __global__ void k_admm_R(const typename Cx<T>::type* __restrict__ H, T* __restri
 }
 
 // ---------------------------------------------------------------------------
-// K4d: GD step size (gd.py:108-112): hmax[c] = max over (dep,ky,kx) |conj(H)*H|_c
+// Per-PSF constants (device, T[4*NC]): [0,NC) hmax  [NC,2NC) psf min  [2NC,3NC) psf max  [3NC,4NC) alpha.
+// NC = C when the plan holds ONE PSF (every sample shares it), NC = B*C when it holds one PSF per sample
+// (LPC_FLAG_PSF_PER_SAMPLE: multi-mask batches, eval/benchmark.py:186-190,255-259).  Column of plane p:
 // ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int lpc_const_col(int p, int DC, int C, int per_sample) {
+    return (per_sample ? (p / DC) * C : 0) + p % C;
+}
+
+// K4d: GD step size (gd.py:108-112): hmax[col] = max over (dep,ky,kx) |conj(H)*H| of that PSF's channel
 template <typename T>
-__global__ void k_hh_max(const typename Cx<T>::type* __restrict__ H, T* __restrict__ hmax, int C, int64_t plane) {
-    // grid: y = psf plane q = dep*C + c
+__global__ void k_hh_max(const typename Cx<T>::type* __restrict__ H, T* __restrict__ hmax, int C, int DC, int per_sample,
+                         int64_t plane) {
+    // grid: y = transfer-function plane q = (s*D + dep)*C + c
     const int q = blockIdx.y;
-    const int c = q % C;
+    const int col = lpc_const_col(q, DC, C, per_sample);
     const typename Cx<T>::type* Hq = H + (int64_t)q * plane;
     T m = T(0);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < plane; i += (int64_t)gridDim.x * blockDim.x) {
@@ -137,45 +145,51 @@ __global__ void k_hh_max(const typename Cx<T>::type* __restrict__ H, T* __restri
         m = tmax(m, h.x * h.x + h.y * h.y);
     }
     m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) atomic_max(&hmax[c], m);
+    if ((threadIdx.x & 31) == 0) atomic_max(&hmax[col], m);
 }
 
-// PSF per-channel min / max over (D,h,w) on the caller's channels-last PSF (gd.py:100-103)
+// PSF per-channel min / max over (D,h,w) on the caller's channels-last PSF (gd.py:100-103); grid (blocks, C, n_psf)
 template <typename T>
 __global__ void k_psf_minmax(const T* __restrict__ psf, int64_t npix, int C, T* __restrict__ vmin, T* __restrict__ vmax) {
-    const int c = blockIdx.y;
+    const int c = blockIdx.y, s = blockIdx.z;
+    psf += (int64_t)s * npix * C;
     T lo = psf[c], hi = psf[c];
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
         T v = psf[i * C + c];
         lo = tmin(lo, v); hi = tmax(hi, v);
     }
     lo = warp_min(lo); hi = warp_max(hi);
-    if ((threadIdx.x & 31) == 0) { atomic_min(&vmin[c], lo); atomic_max(&vmax[c], hi); }
+    if ((threadIdx.x & 31) == 0) { atomic_min(&vmin[s * C + c], lo); atomic_max(&vmax[s * C + c], hi); }
 }
 
-// consts layout (device, T[4*C]): [0,C) hmax  [C,2C) psf min  [2C,3C) psf max  [3C,4C) alpha
+// keep_x0: leave the psf min / max columns alone (UnrolledFISTA keeps the constructor PSF's initial value when a new
+// PSF arrives through forward(psfs=...), trainable_recon.py:347-350 vs unrolled_fista.py:55-59)
 template <typename T>
-__global__ void k_init_consts(T* consts, const T* __restrict__ psf, int C) {
-    int c = threadIdx.x;
-    if (c < C) { consts[c] = T(0); consts[C + c] = psf[c]; consts[2 * C + c] = psf[c]; consts[3 * C + c] = T(0); }
+__global__ void k_init_consts(T* consts, const T* __restrict__ psf, int C, int NC, int64_t npixC, int keep_x0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NC) return;
+    const int s = i / C, c = i - s * C;
+    consts[i] = T(0);
+    consts[3 * NC + i] = T(0);
+    if (!keep_x0) { const T v = psf[(int64_t)s * npixC + c]; consts[NC + i] = v; consts[2 * NC + i] = v; }
 }
 template <typename T>
-__global__ void k_alpha(T* consts, int C, T lip_fact) {
-    int c = threadIdx.x;
-    if (c < C) consts[3 * C + c] = lip_fact / consts[c];
+__global__ void k_alpha(T* consts, int NC, T lip_fact) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NC) consts[3 * NC + i] = lip_fact / consts[i];
 }
 
 // fill the window of planar planes with a per-channel constant: GD initial estimate
 // x0 = (max_c + min_c)/2  (gd.py:99-105)
 template <typename T>
-__global__ void k_fill_x0(T* __restrict__ dst, const T* __restrict__ consts, int C, int h, int w,
-                          int64_t plane_stride, int pitch, int oy, int ox) {
+__global__ void k_fill_x0(T* __restrict__ dst, const T* __restrict__ consts, int C, int DC, int NC, int per_sample, int h,
+                          int w, int64_t plane_stride, int pitch, int oy, int ox) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
     const int y = blockIdx.y;
     const int p = blockIdx.z;
-    const int c = p % C;
-    const T v = (consts[2 * C + c] + consts[C + c]) / T(2);
+    const int col = lpc_const_col(p, DC, C, per_sample);
+    const T v = (consts[2 * NC + col] + consts[NC + col]) / T(2);
     dst[(int64_t)p * plane_stride + (int64_t)(y + oy) * pitch + (x + ox)] = v;
 }
 

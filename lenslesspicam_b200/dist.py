@@ -66,3 +66,66 @@ def barrier(device=None):
 def finalize():
     if dist.is_initialized():
         dist.destroy_process_group()
+
+
+def reconstruct_sharded(host_batch, psf, n_iter=100, algo="admm", chunk=1, gather=False, solver=None,
+                        reconstruct_fn=None, device=None, **solver_kw):
+    """BASELINE configs[3] as a call: reconstruct ``host_batch`` ([N, Dd, h, w, C], host memory, the same tensor on
+    every rank) with the batch axis sharded contiguously over the ranks of the job.
+
+    Every rank takes ``shard_batch(N, world, rank)``, receives rank 0's PSF (the job's ONLY data-path collective,
+    NCCL over NVLink/NVSwitch), builds the solver on its own GPU and streams its shard through
+    ``apply_host_stream`` (H2D / iterations / D2H overlapped, ``chunk`` measurements per launch chain).  No collective
+    runs inside the iteration.  Returns ``(local_out, index_range)`` -- ``local_out`` is this rank's pinned
+    ``[n_local, D, h, w, C]`` -- or, with ``gather=True``, ``(full, index_range)`` where ``full`` is the
+    ``[N, D, h, w, C]`` result on every rank (one all_gather of the padded shards at the end).
+
+    ``solver`` re-uses an existing solver object (its plans and CUDA graphs); ``reconstruct_fn(inputs, outputs)`` replaces
+    the engine call (the CPU tests of the host logic run it under gloo with a stand-in)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    N = int(host_batch.shape[0])
+    mine = shard_batch(N, world, rank)
+    D = int(psf.shape[0])
+    h, w, C = (int(v) for v in host_batch.shape[2:])
+    psf = broadcast_psf(psf, src=0)
+    n_local = len(mine)
+    use_cuda = psf.is_cuda
+
+    def pinned(t):
+        return t.pin_memory() if (use_cuda and not t.is_pinned()) else t
+
+    local_out = pinned(torch.empty((n_local, D, h, w, C), dtype=host_batch.dtype))
+    if n_local:
+        ins, outs = [], []
+        for s in range(0, n_local, max(int(chunk), 1)):
+            e = min(s + max(int(chunk), 1), n_local)
+            ins.append(pinned(host_batch[mine.start + s : mine.start + e].contiguous()))
+            outs.append(local_out[s:e])
+        if reconstruct_fn is not None:
+            reconstruct_fn(ins, outs)
+        else:
+            if solver is None:
+                import lenslesspicam_b200 as L
+
+                cls = {"admm": L.ADMM, "fista": L.FISTA, "gd": L.GradientDescent, "nesterov": L.NesterovGradientDescent}[algo]
+                solver = cls(psf, n_iter=n_iter, **solver_kw)
+            # the last chunk may be smaller: it goes through its own call (its own plan of that batch size)
+            full = [k for k in range(len(ins)) if ins[k].shape[0] == ins[0].shape[0]]
+            solver.apply_host_stream([ins[k] for k in full], [outs[k] for k in full], n_iter=n_iter)
+            rest = [k for k in range(len(ins)) if k not in full]
+            if rest:
+                solver.apply_host_stream([ins[k] for k in rest], [outs[k] for k in rest], n_iter=n_iter)
+    if not gather:
+        return local_out, mine
+    if world == 1:
+        return local_out, mine
+    # all_gather of equally sized (padded) shards, trimmed afterwards; device tensors under NCCL
+    n_max = -(-N // world)
+    dev = device if device is not None else (psf.device if use_cuda else torch.device("cpu"))
+    pad = torch.zeros((n_max, D, h, w, C), dtype=host_batch.dtype, device=dev)
+    pad[:n_local].copy_(local_out, non_blocking=True)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    full = torch.cat([parts[r][: len(shard_batch(N, world, r))] for r in range(world)], dim=0)
+    return full, mine

@@ -24,6 +24,8 @@ Deliberate deviations from the reference, each also in DESIGN.md:
 import abc
 import ctypes
 import pathlib as plib
+import warnings
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -75,6 +77,7 @@ class ReconstructionAlgorithm(abc.ABC):
         # recon.py:263-277 (dtype is a *string* or None in the reference)
         tdtype = get_dtype(dtype, True)
         self._psf = psf.type(tdtype).contiguous()
+        self._psf_ctor = self._psf
         self._dtype = tdtype
         self._complex_dtype = torch.complex64 if tdtype == torch.float32 else torch.complex128
         self._device = self._psf.device
@@ -87,6 +90,7 @@ class ReconstructionAlgorithm(abc.ABC):
         if self._norm not in _lib.NORMS:
             raise ValueError(f"Invalid norm: {self._norm}")
         self._convolver_obj = None
+        self._err_convolver = None  # convolver for reconstruction_error(psfs=...) with PSFs other than the solver's
         lib = _lib.load()
         Hp, Wp, sy, sx = (ctypes.c_int() for _ in range(4))
         D, h, w, C = (int(v) for v in self._psf.shape)
@@ -100,9 +104,13 @@ class ReconstructionAlgorithm(abc.ABC):
             self._image_est_shape = self._padded_shape
 
         self._stream = EngineStream(self._device)
-        self._plans = {}      # batch size -> lpc_plan_t
-        self._plan = None     # plan of the current batch size
+        # (batch size, one-PSF-per-sample) -> lpc_plan_t, least recently used first; at most _MAX_PLANS are kept (a
+        # full-size ADMM plan is ~1.5 GB per image) and none exists until the first call that needs one
+        self._plans = OrderedDict()
+        self._plan = None     # plan of the current batch
         self._B = 1
+        self._per_sample = False
+        self._psfs = None     # [B, D, h, w, C] when the current plan holds one PSF per sample
         self._flags = _lib.FLAG_NO_GRAPH if kwargs.get("no_graph", False) else _lib.FLAG_NONE
         if kwargs.get("engine", None) == "v1":  # K1/K2 + cuFFT instead of the fused own-FFT engine (A/B, bisecting)
             self._flags |= _lib.FLAG_ENGINE_V1
@@ -113,35 +121,90 @@ class ReconstructionAlgorithm(abc.ABC):
             self._initial_est = None
         self._data = None
         self._data_sent = False
+        self._pending_psfs = None  # per-sample PSFs of the batch being sent (forward(batch, psfs))
 
         # used inside trainable recon in the reference; kept for attribute compatibility
         self.compensation_branch = None
         self.compensation_branch_inputs = None
 
-        self._select_plan(1)
         if reset:
             self.reset()
 
     # ------------------------------------------------------------------ plans
-    def _select_plan(self, B):
-        plan = self._plans.get(B)
-        if plan is None:
-            lib = _lib.load()
+    _MAX_PLANS = 2
+    _warned_v1 = False
+
+    def _select_plan(self, B, psfs=None):
+        """Plan for a batch of ``B`` measurements; ``psfs`` ([B, D, h, w, C]) selects a plan that holds one PSF per
+        sample.  New plans get the hyper-parameters, the PSF(s) and a reset."""
+        B = int(B)
+        per_sample = psfs is not None
+        key = (B, per_sample)
+        lib = _lib.load()
+        plan = self._plans.get(key)
+        created = plan is None
+        if created:
+            while len(self._plans) >= self._MAX_PLANS:
+                _, old = self._plans.popitem(last=False)
+                if self._plan is not None and old.value == self._plan.value:
+                    self._plan = None
+                lib.lpc_plan_destroy(old)
             plan = ctypes.c_void_p()
             D, h, w, C = (int(v) for v in self._psf.shape)
+            flags = self._flags | (_lib.FLAG_PSF_PER_SAMPLE if per_sample else 0)
             _lib.check(
                 lib.lpc_plan_create(
                     ctypes.byref(plan), self._dev_index, self._ALGO, torch_dtype_code(self._dtype),
-                    _lib.NORMS[self._norm], int(B), D, C, h, w, self._flags,
+                    _lib.NORMS[self._norm], B, D, C, h, w, flags,
                 )
             )
-            self._plans[B] = plan
+            self._plans[key] = plan
+            if (self._dtype == torch.float32 and lib.lpc_engine_version(plan) != 2 and not (self._flags & _lib.FLAG_ENGINE_V1)
+                    and not ReconstructionAlgorithm._warned_v1):
+                ReconstructionAlgorithm._warned_v1 = True
+                _, Hp, Wp, _ = self._padded_shape
+                warnings.warn(
+                    f"lenslesspicam_b200: padded size {Hp}x{Wp} is not in the fused engine's compiled menu "
+                    "(csrc/lpc_fused.cuh: LPC_ROW_MENU / LPC_COL_MENU); this solver runs the cuFFT-based engine v1, "
+                    "about 2x slower.  `engine_version` on the solver reports which engine serves it.",
+                    RuntimeWarning, stacklevel=3,
+                )
+        self._plans.move_to_end(key)
+        self._plan, self._B, self._per_sample = plan, B, per_sample
+        if created or per_sample:
             with self._stream as st:
-                self._push_params(plan, st)
-                _lib.check(lib.lpc_set_psf(plan, self._psf.data_ptr(), st), plan)
-        self._plan = plan
-        self._B = B
+                if created:
+                    self._push_params(plan, st)
+                    if self._keep_x0:
+                        # the initial value stays the CONSTRUCTOR PSF's whatever PSF arrives later (UnrolledFISTA:
+                        # trainable_recon.py:347-350 swaps the convolver only, unrolled_fista.py:55-59 keeps _image_init)
+                        base = self._psf_ctor if not per_sample else self._psf_ctor[None].expand((B,) + tuple(self._psf_ctor.shape)).contiguous()
+                        _lib.check(lib.lpc_set_psf(plan, base.data_ptr(), st), plan)
+                        _lib.check(lib.lpc_set_option(plan, _lib.OPT_KEEP_X0, 1.0), plan)
+                if per_sample:
+                    self._psfs = psfs.to(device=self._device, dtype=self._dtype).contiguous()
+                    _lib.check(lib.lpc_set_psf(plan, self._psfs.data_ptr(), st), plan)
+                else:
+                    _lib.check(lib.lpc_set_psf(plan, self._psf.data_ptr(), st), plan)
+                if created:
+                    self._after_new_plan(plan, st)
+            self._reset_plan(self._initial_est)
         return plan
+
+    _keep_x0 = False
+
+    def _after_new_plan(self, plan, stream):
+        """hook: parameters that need the PSF on the plan first (unrolled schedules)"""
+
+    def _ensure_plan(self):
+        if self._plan is None:
+            self._select_plan(self._B)
+        return self._plan
+
+    @property
+    def engine_version(self):
+        """2 = fused own-FFT engine (fp32, padded sizes of the compiled menu); 1 = K1/K2/K3 + cuFFT."""
+        return int(_lib.load().lpc_engine_version(self._ensure_plan()))
 
     @abc.abstractmethod
     def _push_params(self, plan, stream):
@@ -152,7 +215,7 @@ class ReconstructionAlgorithm(abc.ABC):
             lib = _lib.load()
             for plan in self._plans.values():
                 lib.lpc_plan_destroy(plan)
-            self._plans = {}
+            self._plans = OrderedDict()
         except Exception:
             pass
 
@@ -187,7 +250,7 @@ class ReconstructionAlgorithm(abc.ABC):
         if Dd not in (1, D) or int(data.shape[4]) != C:
             raise ValueError("data depth must be 1 or the PSF depth, and channels must match the PSF")
         data = data.to(self._dtype)
-        plan = self._select_plan(B)
+        plan = self._select_plan(B, self._pending_psfs)
         lib = _lib.load()
         echo = None
         bg_ptr, bg_strides = None, None
@@ -224,9 +287,16 @@ class ReconstructionAlgorithm(abc.ABC):
         self._initial_est = self._check_est(image_est)
 
     def set_image_estimate(self, image_est):
-        """recon.py:415-442: overwrite the current estimate (warm start without touching _initial_est)."""
+        """recon.py:415-442: overwrite the current estimate, ``_initial_est`` untouched.  Gradient-descent family: exactly
+        that (momentum, t_k and the previous iterate are kept).  ADMM: DEVIATION -- a warm start from ``image_est``
+        (duals re-zeroed); the reference keeps its duals and for one iteration the stale H V / Psi V."""
         est = self._check_est(image_est)
-        self._reset_plan(est)
+        plan = self._ensure_plan()
+        est = est.to(device=self._device, dtype=self._dtype)
+        est = est.expand((self._B,) + tuple(est.shape[1:])).contiguous()
+        lib = _lib.load()
+        with self._stream as st:
+            _lib.check(lib.lpc_set_image_estimate(plan, est.data_ptr(), st), plan)
 
     def get_image_estimate(self):
         """recon.py:444-446 -> [B, D, h, w, C]"""
@@ -239,8 +309,9 @@ class ReconstructionAlgorithm(abc.ABC):
         shape = (self._B, D, Hp, Wp, C) if not self._pad else (self._B,) + tuple(int(v) for v in self._psf.shape)
         out = torch.empty(shape, dtype=self._dtype, device=self._device)
         lib = _lib.load()
+        plan = self._ensure_plan()
         with self._stream as st:
-            _lib.check(lib.lpc_get_state(self._plan, _lib.STATE_IMAGE_EST, out.data_ptr(), st), self._plan)
+            _lib.check(lib.lpc_get_state(plan, _lib.STATE_IMAGE_EST, out.data_ptr(), st), plan)
         return out
 
     def _set_psf(self, psf):
@@ -253,12 +324,18 @@ class ReconstructionAlgorithm(abc.ABC):
             self._convolver_obj.set_psf(self._psf)  # keep its plans: a multi-mask evaluation loop changes the PSF per sample
         lib = _lib.load()
         with self._stream as st:
-            for plan in self._plans.values():
-                _lib.check(lib.lpc_set_psf(plan, self._psf.data_ptr(), st), plan)
+            for (_, per_sample), plan in self._plans.items():
+                if not per_sample:
+                    _lib.check(lib.lpc_set_psf(plan, self._psf.data_ptr(), st), plan)
+        if self._per_sample:  # back to the shared-PSF plan
+            self._plan, self._per_sample, self._psfs = None, False, None
+            self._data_sent = False
         self.reset()
 
     # ------------------------------------------------------------------ iteration
     def _reset_plan(self, initial_est=None):
+        if self._plan is None:
+            return  # no plan yet: a new plan is reset when it is created
         lib = _lib.load()
         ptr = None
         if initial_est is not None:
@@ -275,16 +352,18 @@ class ReconstructionAlgorithm(abc.ABC):
     def _update(self, iter):
         """One iteration (recon.py:338-343); ``apply`` runs all of them in one call instead."""
         lib = _lib.load()
+        plan = self._ensure_plan()
         with self._stream as st:
-            _lib.check(lib.lpc_run(self._plan, 1, st), self._plan)
+            _lib.check(lib.lpc_run(plan, 1, st), plan)
 
     def _form_image(self):
         """admm.py:331-338 / gd.py:136-140 -> fresh [B, D, h, w, C] tensor."""
         D, h, w, C = (int(v) for v in self._psf.shape)
         out = torch.empty((self._B, D, h, w, C), dtype=self._dtype, device=self._device)
         lib = _lib.load()
+        plan = self._ensure_plan()
         with self._stream as st:
-            _lib.check(lib.lpc_get_image(self._plan, out.data_ptr(), st), self._plan)
+            _lib.check(lib.lpc_get_image(plan, out.data_ptr(), st), plan)
         return out
 
     def _progress(self):
@@ -309,7 +388,7 @@ class ReconstructionAlgorithm(abc.ABC):
         """recon.py:498-605.  Extra keyword arguments are accepted and ignored
         (eval/benchmark.py:247-253 passes ``output_intermediate``)."""
         assert self._data is not None, "Must set data with `set_data()`"
-        if background is not None or not self._data_sent or int(self._data.shape[0]) != self._B:
+        if background is not None or not self._data_sent or int(self._data.shape[0]) != self._B or self._plan is None:
             self._send_data(background)
         if reset:
             self.reset()
@@ -363,53 +442,54 @@ class ReconstructionAlgorithm(abc.ABC):
 
     def _forward_batch(self, batch, psfs, background, **apply_kw):
         """``psfs``: None, one PSF ``[D, h, w, C]`` / ``[1, D, h, w, C]``, or one per sample ``[B, D, h, w, C]``
-        (multi-mask datasets, eval/benchmark.py:186-190,255-259).  A plan holds ONE transfer function per
-        (depth, channel), so per-sample PSFs run sample by sample -- ``_set_psf`` costs ~1 ms against a ~50 ms
-        reconstruction (scripts_dev/time_setpsf.py)."""
+        (multi-mask datasets, eval/benchmark.py:186-190,255-259; the reference builds ``RealFFTConvolve2D(psfs)`` with
+        the batch axis kept, trainable_recon.py:347-350).  Per-sample PSFs run as ONE batched launch chain on a plan that
+        holds one transfer function -- and for ADMM one ``R_divmat``, for the gradient-descent family one step size
+        and initial value -- per (sample, depth, channel)."""
         assert isinstance(batch, torch.Tensor) and len(batch.shape) == 5, "batch must be of shape (N, D, H, W, C)"
         apply_kw.setdefault("disp_iter", None)
         apply_kw.setdefault("plot", False)
         B = int(batch.shape[0])
         if psfs is not None and psfs.dim() == 5 and int(psfs.shape[0]) > 1:
             assert int(psfs.shape[0]) == B, "one PSF per sample"
-            outs = []
-            for b in range(B):
-                self._set_psf(psfs[b])
-                self.set_data(batch[b : b + 1])
-                bg = background[b : b + 1] if (background is not None and background.dim() == 5) else background
-                o = self.apply(background=bg, **apply_kw)
-                outs.append(o[None] if self._B == 1 else o)
-            return torch.cat(outs, dim=0)
+            assert tuple(psfs.shape[1:]) == tuple(self._psf.shape), "new PSF must have same shape as old PSF"
+            self._pending_psfs = psfs
+            try:
+                self.set_data(batch)
+                out = self.apply(background=background, **apply_kw)
+            finally:
+                self._pending_psfs = None
+            return out[None] if self._B == 1 else out
         if psfs is not None:
             self._set_psf(psfs[0] if psfs.dim() == 5 else psfs)
+        elif self._per_sample:
+            self._plan, self._per_sample, self._psfs = None, False, None
         self.set_data(batch)
         out = self.apply(background=background, **apply_kw)
         return out[None] if self._B == 1 else out
 
     # ------------------------------------------------------------------ metrics
     def reconstruction_error(self, prediction=None, lensless=None, psfs=None, normalize=True):
-        """recon.py:607-653.  The convolution runs in the engine; the min/max/sum reductions are
-        torch ops (evaluation-loop work, SURVEY 8f.2 -- outside the iteration hot path)."""
+        """recon.py:607-653, on the device in one engine call: convolve (pad -> rfft2 -> H -> irfft2 -> crop), then the
+        min/max normalisation per (batch, depth) and the squared-error sum per batch entry as two fused reduction
+        kernels (csrc/lpc_metrics.cuh).  ``psfs`` may be one PSF or one per sample ``[B, D, h, w, C]``."""
         if prediction is None:
             prediction = self.get_image_estimate()
         if lensless is None:
             lensless = self._data
         if psfs is None:
-            psfs = self._psf
+            psfs = self._psfs if (self._per_sample and self._psfs is not None) else self._psf
         if psfs is self._psf:
             convolver = self._convolver  # cached plan of the solver's own PSF (a benchmark loop calls this per sample)
         else:
-            kw = {k: v for k, v in self._convolver_param.items() if k not in ("no_graph", "engine")}
-            convolver = RealFFTConvolve2D(psfs.to(prediction.device), **kw)
-        if not convolver.pad:
-            prediction = convolver._pad(prediction)
-        Hx = convolver.convolve(prediction)
-        if not convolver.pad:
-            Hx = convolver._crop(Hx)
-        if normalize:
-            Hx = Hx - torch.amin(Hx, dim=(-1, -2, -3), keepdim=True)
-            Hx = Hx / torch.amax(Hx, dim=(-1, -2, -3), keepdim=True)
-        return torch.sum((Hx - lensless) ** 2, dim=(-1, -2, -3, -4)) / self._npix
+            if self._err_convolver is None:
+                kw = {k: v for k, v in self._convolver_param.items() if k not in ("no_graph", "engine")}
+                kw["pad"] = True
+                self._err_convolver = RealFFTConvolve2D(psfs.to(prediction.device), **kw)
+            else:
+                self._err_convolver.set_psf(psfs.to(prediction.device))
+            convolver = self._err_convolver
+        return convolver.reconstruction_error(prediction, lensless, self._npix, normalize=normalize)
 
     # ------------------------------------------------------------------ host-buffer path (bench e2e)
     def apply_host(self, host_data, host_out, n_iter=None):
@@ -493,7 +573,7 @@ class ReconstructionAlgorithm(abc.ABC):
         """Algorithmic HBM bytes one iteration moves for the current batch."""
         lib = _lib.load()
         v = ctypes.c_double()
-        _lib.check(lib.lpc_bytes_per_iter(self._plan, ctypes.byref(v)), self._plan)
+        _lib.check(lib.lpc_bytes_per_iter(self._ensure_plan(), ctypes.byref(v)), self._plan)
         return v.value
 
 

@@ -24,8 +24,8 @@ class RealFFTConvolve2D:
             )
         self.is_torch = True
         assert len(psf.shape) >= 4, "Expected 4D PSF of shape ([batch], depth, width, height, channels)"
-        if len(psf.shape) != 4:
-            raise NotImplementedError("batched PSFs are not supported by the B200 engine")
+        if len(psf.shape) > 5:
+            raise ValueError("Expected a 4D or 5D PSF")
         self._use_3d = psf.shape[-4] != 1
         self._is_rgb = (psf.shape[-1] == 3) if rgb is None else rgb
         assert self._is_rgb or psf.shape[-1] == 1
@@ -45,7 +45,16 @@ class RealFFTConvolve2D:
     # ------------------------------------------------------------------ geometry
     def set_psf(self, psf):
         # rfft_convolve.py:102-131
-        self._psf = psf.type(self.dtype).contiguous()
+        # a 5-D PSF [B, D, h, w, C] is one PSF per batch entry (rfft_convolve.py:121: H keeps the batch axis);
+        # the engine holds it in a plan created with LPC_FLAG_PSF_PER_SAMPLE
+        psf = psf.type(self.dtype).contiguous()
+        n_psf = int(psf.shape[0]) if psf.dim() == 5 else 0
+        if n_psf == 1:
+            psf, n_psf = psf[0], 0
+        if n_psf != getattr(self, "_n_psf", n_psf):
+            self._drop_plans()
+        self._n_psf = n_psf
+        self._psf = psf
         self._psf_shape = np.array(self._psf.shape)
         lib = _lib.load()
         import ctypes
@@ -73,24 +82,32 @@ class RealFFTConvolve2D:
 
             lib = _lib.load()
             plan = ctypes.c_void_p()
-            D, h, w, C = (int(v) for v in self._psf.shape)
+            D, h, w, C = (int(v) for v in self._psf.shape[-4:])
+            if self._n_psf and B != self._n_psf:
+                raise ValueError(f"{self._n_psf} PSFs for a batch of {B}: one PSF per sample is needed")
+            while len(self._plans) >= 2:  # bounded: a plan holds three padded arrays per image
+                lib.lpc_plan_destroy(self._plans.pop(next(iter(self._plans))))
             _lib.check(
                 lib.lpc_plan_create(
                     ctypes.byref(plan), self._psf.device.index or 0, _lib.ALGO_CONV, torch_dtype_code(self.dtype),
-                    _lib.NORMS[self.norm], B, D, C, h, w, _lib.FLAG_NONE,
+                    _lib.NORMS[self.norm], B, D, C, h, w, _lib.FLAG_PSF_PER_SAMPLE if self._n_psf else _lib.FLAG_NONE,
                 )
             )
             self._plans[B] = plan
             self._set_plan_psf(plan)
         return plan
 
-    def __del__(self):
+    def _drop_plans(self):
         try:
             lib = _lib.load()
-            for plan in self._plans.values():
+            for plan in getattr(self, "_plans", {}).values():
                 lib.lpc_plan_destroy(plan)
         except Exception:
             pass
+        self._plans = {}
+
+    def __del__(self):
+        self._drop_plans()
 
     @property
     def _H(self):
@@ -99,8 +116,9 @@ class RealFFTConvolve2D:
             lib = _lib.load()
             D, Hp, Wp, C = self._padded_shape
             cdt = torch.complex64 if self.dtype == torch.float32 else torch.complex128
-            out = torch.empty((D, Hp, Wp // 2 + 1, C), dtype=cdt, device=self._psf.device)
-            plan = self._plan(1)
+            lead = (self._n_psf,) if self._n_psf else ()
+            out = torch.empty(lead + (D, Hp, Wp // 2 + 1, C), dtype=cdt, device=self._psf.device)
+            plan = self._plan(self._n_psf or 1)
             with self._stream as st:
                 _lib.check(lib.lpc_get_H(plan, out.data_ptr(), st), plan)
             self._H_cache = out
@@ -138,9 +156,11 @@ class RealFFTConvolve2D:
         if x.dim() != 5:
             raise ValueError("Expected 4D or 5D tensor")
         D, Hp, Wp, C = self._padded_shape
-        hh, ww = (self._psf.shape[-3], self._psf.shape[-2]) if self.pad else (Hp, Wp)
+        hh, ww = (int(self._psf.shape[-3]), int(self._psf.shape[-2])) if self.pad else (Hp, Wp)
         assert tuple(x.shape[-3:-1]) == (hh, ww), "input spatial shape does not match the convolver"
-        B = x.shape[0]
+        B = int(x.shape[0])
+        if self._n_psf and B == 1:
+            B = self._n_psf  # one input against a batch of PSFs broadcasts over the batch (torch semantics)
         if x.shape[1] not in (1, D) or x.shape[4] not in (1, C):
             raise ValueError("depth / channel axes must be 1 or match the PSF")
         x = x.to(self.dtype)
@@ -170,3 +190,36 @@ class RealFFTConvolve2D:
         if return_fft:
             raise NotImplementedError("return_fft is not exposed by the fused engine")
         return self._apply(y, adjoint=True)
+
+    # ------------------------------------------------------------------ metric
+    def reconstruction_error(self, prediction, lensless, npix, normalize=True):
+        """The arithmetic of ``ReconstructionAlgorithm.reconstruction_error`` (recon.py:607-653) in one call of the
+        engine: pad -> convolve -> crop (with ``pad=False`` the reference pads the prediction itself and crops the
+        result, recon.py:633-638: the same numbers), min/max normalisation per (batch, depth) and the squared-error
+        sum against the measurement as two fused reduction kernels.  Returns ``[B]``."""
+        D, Hp, Wp, C = self._padded_shape
+        h, w = int(self._psf.shape[-3]), int(self._psf.shape[-2])
+        prediction = prediction.to(self.dtype)
+        lensless = lensless.to(device=prediction.device, dtype=self.dtype)
+        while prediction.dim() < 5:
+            prediction = prediction[None]
+        while lensless.dim() < 5:
+            lensless = lensless[None]
+        B = int(prediction.shape[0])
+        assert tuple(prediction.shape[1:]) == (D, h, w, C), "prediction must be [B, D, h, w, C]"
+        Dl = int(lensless.shape[1])
+        assert Dl in (1, D) and tuple(lensless.shape[2:]) == (h, w, C)
+        lensless = lensless.expand(B, Dl, h, w, C).contiguous()
+        prediction = prediction.contiguous()
+        out = torch.empty((B,), dtype=self.dtype, device=prediction.device)
+        lib = _lib.load()
+        plan = self._plan(B)
+        with self._stream as st:
+            _lib.check(
+                lib.lpc_reconstruction_error(
+                    plan, prediction.data_ptr(), lensless.data_ptr(), Dl, 1 if normalize else 0, float(npix),
+                    out.data_ptr(), st,
+                ),
+                plan,
+            )
+        return out

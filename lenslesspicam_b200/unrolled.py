@@ -126,6 +126,11 @@ class UnrolledADMM(_UnrolledMixin, ADMM):
 
 
 class UnrolledFISTA(_UnrolledMixin, FISTA):
+    _keep_x0 = True  # forward(psfs=...) swaps the convolver only; x0 stays the constructor PSF's (unrolled_fista.py:55-59)
+
+    def _after_new_plan(self, plan, stream):
+        self._push_schedule(plan, stream)
+
     def __init__(self, psf, n_iter=5, dtype=None, proj=non_neg, learn_tk=True, tk=1, direct_background_subtraction=False,
                  **kwargs):
         kwargs = _reject_unsupported(dict(kwargs))
@@ -154,11 +159,15 @@ class UnrolledFISTA(_UnrolledMixin, FISTA):
             self._tk_p = torch.as_tensor(t)
 
     def _default_alpha(self):
+        # unrolled_fista.py:60-73: computed ONCE from the constructor PSF (a shared-PSF plan of batch size 1)
         C = int(self._psf.shape[3])
         out = torch.empty((C,), dtype=self._dtype, device=self._device)
         lib = _lib.load()
+        keep = (self._plan, self._B, self._per_sample)
+        plan = self._select_plan(1)
         with self._stream as st:
-            _lib.check(lib.lpc_get_alpha(self._plan, out.data_ptr(), st), self._plan)
+            _lib.check(lib.lpc_get_alpha(plan, out.data_ptr(), st), plan)
+        self._plan, self._B, self._per_sample = keep
         a = out.double().cpu().numpy()  # lip_fact / max|H*H| with lip_fact = 1.8 (gd.py:108-112 == unrolled_fista.py:63-66)
         return torch.as_tensor(np.tile(a[None, :], (self._n_iter, 1)))
 

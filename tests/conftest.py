@@ -20,16 +20,20 @@ def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 
 
+def _wide(a):
+    """float64 / complex128 view of an array (complex values keep their imaginary part)"""
+    a = np.asarray(a)
+    return a.astype(np.complex128) if np.iscomplexobj(a) else a.astype(np.float64)
+
+
 def rel_to_max(a, b):
     """max |a-b| / max |b| -- the parity metric (north_star: 1e-5 relative)."""
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a, b = _wide(a), _wide(b)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
 def rel_l2(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a, b = _wide(a), _wide(b)
     return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
 
 

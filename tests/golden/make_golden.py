@@ -144,6 +144,77 @@ def make_unrolled(lensless, torch):
     print("wrote unrolled.npz", {k: v.shape for k, v in store.items()})
 
 
+def make_bundled_large(lensless, torch):
+    """BASELINE configs[0] at the sizes the reference's own scripts use:
+
+    * ``bundled_ds8.npz``      ``load_data(downsample=8)`` RGB -> 3x380x507 (padded 768x1024): ADMM-5 / ADMM-100 /
+                               FISTA-300 of the reference's torch-fp32 path, plus ``reconstruction_error`` values
+    * ``bundled_ds4_gray.npz`` ``load_data(downsample=4, gray=True)`` -> 1x760x1014 (padded 1536x2048), the settings of
+                               profile/admm.py:12-16 and profile/gradient_descent.py:12-16 (the JOSS paper's table)
+
+    fp64 truths are NOT stored (size): the GPU tests recompute them with oracle/lensless_oracle_torch.py in fp64,
+    which tests/test_oracle_golden.py pins against the fp64 goldens of the small cases."""
+    from lensless.utils.io import load_data
+
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        sets = {}
+        for name, kw in (("bundled_ds8", dict(downsample=8)), ("bundled_ds4_gray", dict(downsample=4, gray=True))):
+            psf, data = load_data(psf_fp="data/psf/tape_rgb.png", data_fp="data/raw_data/thumbs_up_rgb.png",
+                                  plot=False, dtype="float32", normalize=True, **kw)
+            sets[name] = (np.asarray(psf, dtype=np.float32), np.asarray(data, dtype=np.float32))
+    finally:
+        os.chdir(cwd)
+    for name, (psf, data) in sets.items():
+        store = {"psf": psf, "data": data}
+        for n in (5, 100):
+            store[f"admm_t32_{n}"] = run_ref(lensless, torch, "ADMM", psf, data, (n,), "t32")[n]
+        store["fista_t32_300"] = run_ref(lensless, torch, "FISTA", psf, data, (300,), "t32")[300]
+        # reconstruction_error (recon.py:607-653) of the reference on its own ADMM-5 state, both normalisations
+        rec = lensless.ADMM(torch.from_numpy(psf.copy()))
+        rec.set_data(torch.from_numpy(data.copy()))
+        rec.apply(n_iter=5, disp_iter=None, plot=False)
+        store["admm5_recon_error_norm"] = rec.reconstruction_error(normalize=True).numpy().copy()
+        store["admm5_recon_error_raw"] = rec.reconstruction_error(normalize=False).numpy().copy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+        print("wrote", name + ".npz", psf.shape, data.shape,
+              {k: float(np.abs(v).max()) for k, v in store.items() if k.startswith(("admm", "fista"))})
+
+
+def make_recon_error(lensless, torch):
+    """``recon_error.npz``: reconstruction_error (recon.py:607-653) of ADMM (pad=False branch) and FISTA (pad=True
+    branch) on a small case, normalised and raw, default arguments and explicit (prediction, lensless, psfs)."""
+    psf, data = synth(24, 32, 3, 12)
+    psf2, _ = synth(24, 32, 3, 13)
+    store = {"psf": psf, "data": data, "psf2": psf2}
+    for key, cls in (("admm", lensless.ADMM), ("fista", lensless.FISTA)):
+        rec = cls(torch.from_numpy(psf.copy()))
+        rec.set_data(torch.from_numpy(data.copy()))
+        rec.apply(n_iter=10, disp_iter=None, plot=False)
+        store[f"{key}_err_norm"] = rec.reconstruction_error(normalize=True).numpy().copy()
+        store[f"{key}_err_raw"] = rec.reconstruction_error(normalize=False).numpy().copy()
+        pred = rec.get_image_estimate().clone()
+        store[f"{key}_pred"] = pred.numpy().copy()
+        store[f"{key}_err_psf2"] = rec.reconstruction_error(prediction=pred, lensless=torch.from_numpy(data[None].copy()),
+                                                            psfs=torch.from_numpy(psf2.copy())).numpy().copy()
+    # set_image_estimate (recon.py:415-442) mid-run and right after a reset, gradient-descent family
+    rng = np.random.default_rng(77)
+    est = rng.random((1, 1, 24, 32, 3)).astype(np.float32) * 0.5
+    store["est"] = est
+    for key, cls in (("gd", lensless.GradientDescent), ("nesterov", lensless.NesterovGradientDescent), ("fista", lensless.FISTA)):
+        rec = cls(torch.from_numpy(psf.copy()))
+        rec.set_data(torch.from_numpy(data.copy()))
+        rec.apply(n_iter=3, disp_iter=None, plot=False)
+        rec.set_image_estimate(torch.from_numpy(est.copy()))
+        store[f"{key}_setest_mid"] = rec.apply(n_iter=4, disp_iter=None, plot=False, reset=False).numpy().copy()
+        rec.reset()
+        rec.set_image_estimate(torch.from_numpy(est.copy()))
+        store[f"{key}_setest_fresh"] = rec.apply(n_iter=4, disp_iter=None, plot=False, reset=False).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "recon_error.npz"), **store)
+    print("wrote recon_error.npz", {k: v for k, v in store.items() if "err" in k})
+
+
 def main():
     lensless = _import_reference()
     import torch
@@ -151,6 +222,11 @@ def main():
     if "--only-unrolled" in sys.argv:
         torch.manual_seed(0)
         return make_unrolled(lensless, torch)
+    if "--only-bundled-large" in sys.argv:
+        torch.set_num_threads(8)
+        return make_bundled_large(lensless, torch)
+    if "--only-recon-error" in sys.argv:
+        return make_recon_error(lensless, torch)
 
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -268,6 +344,8 @@ def main():
         store[f"fista_{backend}_20"] = run_ref(lensless, torch, "FISTA", psf, data, (20,), backend)[20]
     np.savez_compressed(os.path.join(HERE, "bundled_ds16.npz"), **store)
     print("wrote bundled_ds16.npz", psf.shape, data.shape)
+    make_bundled_large(lensless, torch)
+    make_recon_error(lensless, torch)
 
 
 if __name__ == "__main__":

@@ -335,6 +335,47 @@ def test_set_psf_and_reconstruction_error():
     assert err.shape == (1,) and torch.isfinite(err).all()
 
 
+def test_reconstruction_error_matches_reference():
+    """recon.py:607-653 against the reference's own values (tests/golden/recon_error.npz): the ADMM branch
+    (pad=False: pad -> convolve -> crop) and the gradient-descent branch (pad=True), normalised and raw, default
+    arguments (current estimate, set data, own PSF) and explicit (prediction, lensless, psfs)."""
+    g = load_golden("recon_error")
+    for algo in ("admm", "fista"):
+        res, rec = run(algo, g["psf"], g["data"], 10)
+        for norm, key in ((True, "err_norm"), (False, "err_raw")):
+            err = rec.reconstruction_error(normalize=norm)
+            assert err.dtype == torch.float32 and tuple(err.shape) == g[f"{algo}_{key}"].shape
+            np.testing.assert_allclose(err.cpu().numpy(), g[f"{algo}_{key}"], rtol=1e-4)
+        # explicit arguments on the reference's own prediction: only the metric's arithmetic differs
+        err = rec.reconstruction_error(prediction=dev(g[f"{algo}_pred"]), lensless=dev(g["data"][None]), psfs=dev(g["psf2"]))
+        np.testing.assert_allclose(err.cpu().numpy(), g[f"{algo}_err_psf2"], rtol=2e-5)
+        err = rec.reconstruction_error(prediction=dev(g[f"{algo}_pred"]), lensless=dev(g["data"][None]), normalize=True)
+        np.testing.assert_allclose(err.cpu().numpy(), g[f"{algo}_err_norm"], rtol=2e-5)
+    # batched prediction with one PSF per sample == the per-sample values
+    preds = torch.cat([dev(g["admm_pred"]), dev(g["fista_pred"])])
+    psfs = torch.stack([dev(g["psf2"]), dev(g["psf"])])
+    lens = torch.cat([dev(g["data"][None]), dev(g["data"][None])])
+    err = rec.reconstruction_error(prediction=preds, lensless=lens, psfs=psfs)
+    np.testing.assert_allclose(err.cpu().numpy(), [g["admm_err_psf2"][0], g["fista_err_norm"][0]], rtol=2e-5)
+
+
+def test_set_image_estimate_keeps_momentum_like_the_reference():
+    """recon.py:415-442 overwrites the iterate only: Nesterov's p, FISTA's t_k and previous iterate survive; right after
+    a reset FISTA's previous iterate stops aliasing the estimate (gd.py:233)."""
+    g = load_golden("recon_error")
+    for algo in ("gd", "nesterov", "fista"):
+        rec = getattr(L(), ALGOS[algo])(dev(g["psf"]))
+        rec.set_data(dev(g["data"]))
+        rec.apply(n_iter=3, disp_iter=None, plot=False)
+        rec.set_image_estimate(dev(g["est"]))
+        out = rec.apply(n_iter=4, disp_iter=None, plot=False, reset=False)
+        assert rel_to_max(out.cpu().numpy(), g[f"{algo}_setest_mid"]) <= TOL, algo
+        rec.reset()
+        rec.set_image_estimate(dev(g["est"]))
+        out = rec.apply(n_iter=4, disp_iter=None, plot=False, reset=False)
+        assert rel_to_max(out.cpu().numpy(), g[f"{algo}_setest_fresh"]) <= TOL, algo
+
+
 def test_host_buffer_path_matches_device_path():
     g = load_golden("small_even_rgb")
     rec = L().ADMM(dev(g["psf"]))
@@ -477,6 +518,23 @@ def test_forward_with_per_sample_psfs_matches_individual_runs():
     # one shared PSF given as [1, D, h, w, C] is the batched path
     out1 = rec.forward(batch=batch, psfs=dev(g["psf"])[None])
     assert rel_to_max(out1.cpu().numpy(), g["admm_t32_10"]) <= TOL
+    # against the CPU oracle sample by sample (per-sample H and R_divmat / step size and initial value)
+    for algo, n in (("admm", 10), ("fista", 10), ("nesterov", 6)):
+        rec = getattr(L(), ALGOS[algo])(dev(g["psf"]), n_iter=n)
+        out = rec.forward(batch=batch, psfs=dev(psfs)).cpu().numpy()
+        for b in range(4):
+            ref = orc.reconstruct(algo, psfs[b], g["batch"][b], n)
+            assert rel_to_max(out[b], ref) <= TOL, (algo, b)
+        # back to the constructor's shared PSF
+        out1 = rec.forward(batch=batch).cpu().numpy()
+        assert rel_to_max(out1[2], orc.reconstruct(algo, g["psf"], g["batch"][2], n)) <= TOL, algo
+    # the convolver with a batch of PSFs (rfft_convolve.py:121 keeps the batch axis of H)
+    conv = L().RealFFTConvolve2D(dev(psfs), pad=True, norm="backward")
+    full = conv.convolve(batch).cpu().numpy()
+    for b in range(4):
+        one = orc.OracleConvolver(psfs[b], pad=True, norm="backward").convolve(g["batch"][b : b + 1])
+        assert rel_to_max(full[b : b + 1], one) <= TOL
+    assert tuple(conv._H.shape) == (4, 1, 48, 33, 3)
 
 
 def test_host_stream_matches_device_path():
