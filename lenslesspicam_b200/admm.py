@@ -67,6 +67,74 @@ class ADMM(ReconstructionAlgorithm):
         _lib.check(lib.lpc_set_admm_params(plan, self._mu1, self._mu2, self._mu3, self._tau, stream), plan)
 
 
+# ---------------------------------------------------------------------------------------------
+# module-level helpers (admm.py:341-397; unrolled_admm.py:10 and user code import them).  Inside the solvers they are
+# fused into the spatial kernels; these are the stand-alone forms, each one hand-written kernel (csrc/lpc_ops.cuh).
+# ---------------------------------------------------------------------------------------------
+def _op_args(x):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise TypeError("lenslesspicam_b200 helpers need CUDA tensors (the reference's own functions serve numpy / CPU)")
+    if x.dtype not in (torch.float32, torch.float64):
+        raise TypeError("float32 / float64 only")
+    x = x.contiguous()
+    from ._engine import torch_dtype_code
+
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    return x, dev, torch_dtype_code(x.dtype), torch.cuda.current_stream(x.device).cuda_stream
+
+
+def soft_thresh(x, thresh):
+    """admm.py:341-346: ``sign(x) * max(|x| - thresh, 0)``"""
+    x, dev, code, st = _op_args(x)
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().lpc_op_soft_thresh(dev, code, x.data_ptr(), out.data_ptr(), x.numel(), float(thresh), st))
+    return out
+
+
+def finite_diff(x):
+    """admm.py:349-359: periodic backward differences along H (-3) and W (-2), stacked on a new last axis."""
+    x, dev, code, st = _op_args(x)
+    assert x.dim() >= 3, "expected [..., H, W, C]"
+    H, W, C = (int(v) for v in x.shape[-3:])
+    outer = x.numel() // max(H * W * C, 1)
+    out = torch.empty(tuple(x.shape) + (2,), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().lpc_op_finite_diff(dev, code, x.data_ptr(), out.data_ptr(), outer, H, W, C, st))
+    return out
+
+
+def finite_diff_adj(x):
+    """admm.py:362-370: adjoint of :func:`finite_diff` -- ``[..., H, W, C, 2] -> [..., H, W, C]``"""
+    x, dev, code, st = _op_args(x)
+    assert x.dim() >= 4 and x.shape[-1] == 2, "expected [..., H, W, C, 2]"
+    H, W, C = (int(v) for v in x.shape[-4:-1])
+    outer = x.numel() // max(2 * H * W * C, 1)
+    out = torch.empty(tuple(x.shape[:-1]), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().lpc_op_finite_diff_adj(dev, code, x.data_ptr(), out.data_ptr(), outer, H, W, C, st))
+    return out
+
+
+def finite_diff_gram(shape, dtype=None, is_torch=True, device=None):
+    """admm.py:373-397: ``rfft2`` of the finite-difference Gram stencil for a padded shape ``[D, Hp, Wp, C]``, evaluated in
+    closed form (``4 - 2cos(2 pi ky/Hp) - 2cos(2 pi kx/Wp)``; the reference's depth > 1 variant included).  Complex
+    ``[D, Hp, Wp//2+1, C]`` on ``device`` (default: the current CUDA device; the reference returns a CPU tensor that
+    ``ADMM.__init__`` then moves to the PSF's device, admm.py:122-123)."""
+    if not is_torch:
+        raise TypeError("no numpy path in lenslesspicam_b200")
+    from .recon import get_dtype
+    from ._engine import torch_dtype_code
+
+    if dtype is None or isinstance(dtype, str):
+        dtype = get_dtype(dtype, True)
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    D, Hp, Wp, C = (int(v) for v in shape)
+    cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+    out = torch.empty((D, Hp, Wp // 2 + 1, C), dtype=cdt, device=device)
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    st = torch.cuda.current_stream(device).cuda_stream
+    _lib.check(_lib.load().lpc_op_finite_diff_gram(dev, torch_dtype_code(dtype), out.data_ptr(), D, Hp, Wp, C, st))
+    return out
+
+
 def apply_admm(psf, data, n_iter, verbose=False, **kwargs):
     """admm.py:400-419 with tensors instead of file paths (loading images is the reference's job)."""
     recon = ADMM(psf, n_iter=n_iter, **kwargs)

@@ -4,6 +4,7 @@
 // graph of the iteration loop.  No torch types, no exceptions across the boundary.
 #include "../../include/lpc.h"
 
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +21,7 @@
 #include "lpc_fused_tma.cuh"
 #include "lpc_gd.cuh"
 #include "lpc_metrics.cuh"
+#include "lpc_ops.cuh"
 #include "lpc_setup.cuh"
 #include "lpc_util.cuh"
 
@@ -462,6 +464,12 @@ struct Plan : lpc_plan_s {
     int ry_log2 = 0;       // B2 processes 1 << ry_log2 rows per CTA (measured: 1 row 315 us, 2 rows 400, 4 rows 465)
     int cols_variant = 1;  // A: 0 = 1024 threads x 1 CTA/SM, 1 = 576 threads x 2 CTAs/SM
 
+    // power-of-two balancing of the two-for-one row packings (FusedK::pack_s / pack_t), as log2 exponents
+    int pack_s_fixed = INT_MIN, pack_t_fixed = INT_MIN;  // LPC_PACK_S / LPC_PACK_T: overrides of the automatic choice
+    float* pack_dev = nullptr;  // {pack_t, 1/pack_t}, written per PSF by k_pack_scale
+    void set_pack_scales(int es) {
+        fk.pack_s = std::ldexp(1.0f, es); fk.inv_pack_s = std::ldexp(1.0f, -es);
+    }
     int next_dir() { const int d = dir_enable ? dir_toggle : 0; dir_toggle ^= 1; return d; }
     int launch_rows_ifft(cudaStream_t st, int p0 = 0, int np = -1, T* vh = nullptr) {
         if constexpr (std::is_same<T, float>::value) {
@@ -548,6 +556,11 @@ struct Plan : lpc_plan_s {
             if (const char* e = getenv("LPC_COLS_VARIANT")) cols_variant = atoi(e) ? 1 : 0;
 
             fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;
+            if (const char* e = getenv("LPC_PACK_S")) pack_s_fixed = atoi(e);
+            if (const char* e = getenv("LPC_PACK_T")) pack_t_fixed = atoi(e);
+            set_pack_scales(pack_s_fixed == INT_MIN ? 0 : pack_s_fixed);
+            { int rc0; if ((rc0 = alloc(&pack_dev, 2))) return rc0; fk.pack = pack_dev; }
+            { const float one[2] = {1.f, 1.f}; LPC_CK(cudaMemcpy(pack_dev, one, sizeof one, cudaMemcpyHostToDevice)); }
             fk.n_planes = Np; fk.DC = PQ;
             int rc;
             const size_t tsz = (size_t)Np * fk.NT * Hp * 2 * LPC_NCT;
@@ -865,6 +878,10 @@ struct Plan : lpc_plan_s {
             LPC_KCHECK();
         }
         if ((rc = compute_alpha(st))) return rc;
+        if (v2) {
+            k_pack_scale<T><<<1, 32, 0, st>>>(consts, NC, pack_dev, pack_t_fixed == INT_MIN ? -100000 : pack_t_fixed);
+            LPC_KCHECK();
+        }
         if (algo == LPC_ALGO_ADMM && (rc = compute_R(st))) return rc;
         if (gd2) {
             k_gd_tile_filter<T><<<1184, 256, 0, st>>>(Hc, Sy, Sx, Fg, PQ, Hp, Wp, Nh, gk.NTg);
@@ -1679,6 +1696,50 @@ int lpc_set_option(lpc_plan_t plan, int option, double value) {
     LPC_NEED(plan);
     return plan->set_option(option, value);
 }
+// ---- module-level helpers of admm.py as plan-less entry points (lpc_ops.cuh)
+#define LPC_OP_PROLOGUE(devidx)                                    \
+    if (dtype != LPC_F32 && dtype != LPC_F64) return LPC_EINVAL;   \
+    DeviceGuard lpc_guard_(devidx);                                \
+    cudaStream_t st = (cudaStream_t)stream
+#define LPC_OP_EPILOGUE() return cudaGetLastError() == cudaSuccess ? LPC_OK : LPC_ECUDA
+static inline unsigned op_blocks(int64_t n) { int64_t b = (n + 255) / 256; return (unsigned)(b < 1 ? 1 : (b > 148 * 32 ? 148 * 32 : b)); }
+
+int lpc_op_soft_thresh(int device, int dtype, const void* dev_x, void* dev_out, int64_t n, double thresh, void* stream) {
+    if (!dev_x || !dev_out || n < 0) return LPC_EINVAL;
+    LPC_OP_PROLOGUE(device);
+    if (n == 0) return LPC_OK;
+    if (dtype == LPC_F32) k_op_soft_thresh<float><<<op_blocks(n), 256, 0, st>>>((const float*)dev_x, (float*)dev_out, n, (float)thresh);
+    else k_op_soft_thresh<double><<<op_blocks(n), 256, 0, st>>>((const double*)dev_x, (double*)dev_out, n, thresh);
+    LPC_OP_EPILOGUE();
+}
+int lpc_op_finite_diff(int device, int dtype, const void* dev_x, void* dev_out, int64_t outer, int H, int W, int C, void* stream) {
+    if (!dev_x || !dev_out || outer < 0 || H < 1 || W < 1 || C < 1) return LPC_EINVAL;
+    LPC_OP_PROLOGUE(device);
+    const int64_t n = outer * H * W * C;
+    if (n == 0) return LPC_OK;
+    if (dtype == LPC_F32) k_op_finite_diff<float><<<op_blocks(n), 256, 0, st>>>((const float*)dev_x, (float*)dev_out, outer, H, W, C);
+    else k_op_finite_diff<double><<<op_blocks(n), 256, 0, st>>>((const double*)dev_x, (double*)dev_out, outer, H, W, C);
+    LPC_OP_EPILOGUE();
+}
+int lpc_op_finite_diff_adj(int device, int dtype, const void* dev_u, void* dev_out, int64_t outer, int H, int W, int C, void* stream) {
+    if (!dev_u || !dev_out || outer < 0 || H < 1 || W < 1 || C < 1) return LPC_EINVAL;
+    LPC_OP_PROLOGUE(device);
+    const int64_t n = outer * H * W * C;
+    if (n == 0) return LPC_OK;
+    if (dtype == LPC_F32) k_op_finite_diff_adj<float><<<op_blocks(n), 256, 0, st>>>((const float*)dev_u, (float*)dev_out, outer, H, W, C);
+    else k_op_finite_diff_adj<double><<<op_blocks(n), 256, 0, st>>>((const double*)dev_u, (double*)dev_out, outer, H, W, C);
+    LPC_OP_EPILOGUE();
+}
+int lpc_op_finite_diff_gram(int device, int dtype, void* dev_out, int D, int Hp, int Wp, int C, void* stream) {
+    if (!dev_out || D < 1 || Hp < 1 || Wp < 1 || C < 1) return LPC_EINVAL;
+    LPC_OP_PROLOGUE(device);
+    const int Nh = Wp / 2 + 1;
+    const int64_t n = (int64_t)D * Hp * Nh * C;
+    if (dtype == LPC_F32) k_op_finite_diff_gram<float><<<op_blocks(n), 256, 0, st>>>((float2*)dev_out, D, Hp, Wp, Nh, C);
+    else k_op_finite_diff_gram<double><<<op_blocks(n), 256, 0, st>>>((double2*)dev_out, D, Hp, Wp, Nh, C);
+    LPC_OP_EPILOGUE();
+}
+
 int lpc_bytes_per_iter(lpc_plan_t plan, double* algorithmic_bytes) {
     LPC_NEED(plan);
     if (!algorithmic_bytes) return LPC_EINVAL;

@@ -58,6 +58,17 @@ struct FusedK {
     int pf;      // B2: L2-prefetch distance in rows (0 = off), see k_rows_spatial_fft
     int rev;     // 1: walk rows / tiles and planes in DESCENDING order.  Consecutive launches alternate, so a kernel
                  // starts on what its predecessor wrote last -- the part of the hand-off still in the 126 MB L2
+    // Two real signals share one complex row transform (z = a + i*xi', Y = Vhat + i*HVhat), and a transform's round-off
+    // lands on BOTH outputs in proportion to the LARGER input: H V carries the PSF's DC gain (sum(psf)/||psf||, a few
+    // hundred for an L2-normalised PSF) over V, `a` is ~mu3/mu1 times xi'.  The smaller partner is therefore scaled up
+    // by an exact power of two before packing and down after separation (no rounding either way), so each signal sees
+    // round-off relative to its own magnitude.  Measured at 3x1080x1920 (rms HV / rms V = 126, DC gain 381), error of
+    // ADMM-100 against the fp64 reference: pack_t = 1: 2.4e-4, 2^4: 7.8e-5, 2^6: 8.5e-5, 2^8: 1.0e-4 (the reference's own
+    // fp32 arithmetic: 1.8e-4; the cuFFT engine, which transforms V and HV separately: 5.8e-5); `a` and xi' turned out
+    // balanced already (rms 4.4e-7 / 3.2e-7), pack_s = 1.  profiles/README.md, "packing balance".
+    float pack_s, inv_pack_s;  // B2: z = a + i*(pack_s*xi'); separation multiplies Xi by inv_pack_s
+    const float* pack;         // device {pack_t, 1/pack_t}: B1 transforms Y = pack_t*Vhat + i*HVhat and stores V * (1/pack_t);
+                               // chosen per PSF on the device (k_pack_scale): 2^(round(log2(sqrt(max|H|^2))) - 3), >= 1
 };
 // logical (row or tile, plane) of a CTA under the launch's direction
 __device__ __forceinline__ int lpc_dir_x(const FusedK& f, int n) { return f.rev ? n - 1 - (int)blockIdx.x : (int)blockIdx.x; }
@@ -70,7 +81,7 @@ constexpr int LPC_ROWS_RY = 4;  // rows a B2 CTA processes back to back
 template <typename T, typename SEQ>
 __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const typename CxT<T>::type* __restrict__ tw,
                                                typename CxT<T>::type* __restrict__ Tdst, int64_t tile_stride, int row,
-                                               int NT, T sep_scale, int tid) {
+                                               int NT, T sep_scale, int tid, T sep_scale_im) {
     using C = typename CxT<T>::type;
     constexpr int NTH = LPC_ROWS_THREADS, NCT = LPC_NCT, Wp = SEQ::N, Nh = Wp / 2 + 1, PADSH = SEQ::padsh;
     CtaFftStatic<T, SEQ, -1, 1, NTH>::run(W, tw, tid);
@@ -86,8 +97,8 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
                 const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PADSH)];
                 o.v[0] = (zk.x + zm.x) * sep_scale;  // A  = Z[k] + conj(Z[-k])
                 o.v[1] = (zk.y - zm.y) * sep_scale;
-                o.v[2] = (zk.y + zm.y) * sep_scale;  // Xi = (Z[k] - conj(Z[-k])) / i
-                o.v[3] = (zm.x - zk.x) * sep_scale;
+                o.v[2] = (zk.y + zm.y) * sep_scale_im;  // Xi = (Z[k] - conj(Z[-k])) / i
+                o.v[3] = (zm.x - zk.x) * sep_scale_im;
             }
             st16_hint(reinterpret_cast<T*>(Tdst + (int64_t)(kx / NCT) * tile_stride + (int64_t)row * (2 * NCT) + (kx % NCT) * 2), o,
                       LPC_L2_EVICT_LAST);  // the column kernel reads it next
@@ -104,8 +115,8 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
                     const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PADSH)];
                     a[c].x = (zk.x + zm.x) * sep_scale;  // Z[k] + conj(Z[-k])
                     a[c].y = (zk.y - zm.y) * sep_scale;
-                    x[c].x = (zk.y + zm.y) * sep_scale;  // (Z[k] - conj(Z[-k])) / i
-                    x[c].y = (zm.x - zk.x) * sep_scale;
+                    x[c].x = (zk.y + zm.y) * sep_scale_im;  // (Z[k] - conj(Z[-k])) / i
+                    x[c].y = (zm.x - zk.x) * sep_scale_im;
                 }
             }
             C* dst = Tdst + (int64_t)t * tile_stride + (int64_t)row * (2 * NCT);
@@ -139,6 +150,7 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     // one COLUMN per lane: the 16-byte piece (Vhat[kx], HVhat[kx]) of the 32-byte chunk (two adjacent lanes share a
     // sector: 16 lines per warp instruction, unit-stride shared-memory stores); all pieces in flight at once
     static_assert(sizeof(T) == 4 && NCT == 2, "the fused engine is float-only with 32-byte chunks");
+    const float2 pk = __ldg(reinterpret_cast<const float2*>(f.pack));  // {pack_t, 1/pack_t}
     constexpr int NK = NT * NCT;
     constexpr int IT = (NK + NTH - 1) / NTH;
     Vec16<T> pc[IT];
@@ -152,7 +164,7 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
     for (int it = 0; it < IT; ++it) {
         const int kx = tid + it * NTH;
         if (kx < Nh) {
-            const T vx = pc[it].v[0], vy = pc[it].v[1], hx = pc[it].v[2], hy = pc[it].v[3];
+            const T vx = pc[it].v[0] * pk.x, vy = pc[it].v[1] * pk.x, hx = pc[it].v[2], hy = pc[it].v[3];
             C y; y.x = vx - hy; y.y = vy + hx;
             W[fft_pad(kx, PADSH)] = y;
             const int m = Wp - kx;
@@ -178,7 +190,7 @@ k_rows_ifft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const typena
         fft_bfly_compute<T, RL, +1>(v, tw + TR::tw_off_last, NSL, j);
 #pragma unroll
         for (int m = 0; m < RL; ++m) {  // B2 reads them next
-            st4_hint(Vout + j + m * NSL, v[m].x, LPC_L2_EVICT_LAST);
+            st4_hint(Vout + j + m * NSL, v[m].x * pk.y, LPC_L2_EVICT_LAST);
             st4_hint(HVout + j + m * NSL, v[m].y, LPC_L2_EVICT_LAST);
         }
     }
@@ -199,10 +211,11 @@ k_rows_fft(FusedK f, const typename CxT<T>::type* __restrict__ tw, const T* __re
     const int64_t plane = (int64_t)f.Hp * Wp;
     const T* Vin = VH + (int64_t)p * plane + (int64_t)row * Wp;
     const T* HVin = Vin + (int64_t)f.n_planes * plane;
-    for (int j = tid; j < Wp; j += NTH) { C z; z.x = Vin[j]; z.y = HVin[j]; W[fft_pad(j, PADSH)] = z; }
+    const float2 pk = __ldg(reinterpret_cast<const float2*>(f.pack));  // balance the packing (see FusedK::pack)
+    for (int j = tid; j < Wp; j += NTH) { C z; z.x = Vin[j] * pk.x; z.y = HVin[j]; W[fft_pad(j, PADSH)] = z; }
     __syncthreads();
     const int64_t tile_stride = (int64_t)f.Hp * (2 * NCT);
-    rows_fft_store<T, SEQ>(W, tw, Tin + (int64_t)p * NT * tile_stride, tile_stride, row, NT, sep_scale, tid);
+    rows_fft_store<T, SEQ>(W, tw, Tin + (int64_t)p * NT * tile_stride, tile_stride, row, NT, sep_scale * pk.y, tid, sep_scale);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,13 +305,13 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                     }
                     if constexpr (PADSH >= 30) {  // z = a + i*xi' for 4 pixels as two 16-byte shared stores
                         Vec16<T> lo, hi;
-                        lo.v[0] = av[0]; lo.v[1] = xin.v[0]; lo.v[2] = av[1]; lo.v[3] = xin.v[1];
-                        hi.v[0] = av[2]; hi.v[1] = xin.v[2]; hi.v[2] = av[3]; hi.v[3] = xin.v[3];
+                        lo.v[0] = av[0]; lo.v[1] = xin.v[0] * f.pack_s; lo.v[2] = av[1]; lo.v[3] = xin.v[1] * f.pack_s;
+                        hi.v[0] = av[2]; hi.v[1] = xin.v[2] * f.pack_s; hi.v[2] = av[3]; hi.v[3] = xin.v[3] * f.pack_s;
                         *reinterpret_cast<Vec16<T>*>(W + j) = lo;
                         *reinterpret_cast<Vec16<T>*>(W + j + 2) = hi;
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { C z; z.x = av[e]; z.y = xin.v[e]; W[fft_pad(j + e, PADSH)] = z; }
+                        for (int e = 0; e < 4; ++e) { C z; z.x = av[e]; z.y = xin.v[e] * f.pack_s; W[fft_pad(j + e, PADSH)] = z; }
                     }
                     st16_hint(xip + ro + j, xin, LPC_L2_STREAM);  // the duals are not touched again for a whole iteration
                     st16_hint(rhop + ro + j, rhon, LPC_L2_STREAM);
@@ -327,7 +340,7 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                 eta1_o[ro + j] = e1n;
                 C z;
                 z.x = -rhon + ((t0d - t0) + (t1r - t1));
-                z.y = xin;
+                z.y = xin * f.pack_s;
                 W[fft_pad(j, PADSH)] = z;
             }
         }
@@ -348,7 +361,7 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                     for (int l = tid; l < LPR; l += NTH) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rows6[a]) + (size_t)l * 128));
             }
         }
-        rows_fft_store<T, SEQ>(W, tw, ToutP, tile_stride, i, NT, T(1), tid);
+        rows_fft_store<T, SEQ>(W, tw, ToutP, tile_stride, i, NT, T(1), tid, f.inv_pack_s);
     }
 }
 

@@ -179,6 +179,22 @@ __global__ void k_alpha(T* consts, int NC, T lip_fact) {
     if (i < NC) consts[3 * NC + i] = lip_fact / consts[i];
 }
 
+// power-of-two balance of the fused engine's (V, HV) row packing (FusedK::pack): {t, 1/t} with
+// t = 2^clamp(round(log2(sqrt(max |H|^2))) - 3, 0, 24); fixed_exp >= 0 overrides the exponent (LPC_PACK_T)
+template <typename T>
+__global__ void k_pack_scale(const T* __restrict__ consts, int NC, float* __restrict__ pack, int fixed_exp) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T m = T(0);
+    for (int i = 0; i < NC; ++i) m = tmax(m, consts[i]);
+    int e = 0;
+    if (m > T(0)) e = (int)lrint(0.5 * log2((double)m)) - 3;
+    if (e < 0) e = 0;
+    if (e > 24) e = 24;
+    if (fixed_exp > -1000) e = fixed_exp;
+    pack[0] = ldexpf(1.0f, e);
+    pack[1] = ldexpf(1.0f, -e);
+}
+
 // fill the window of planar planes with a per-channel constant: GD initial estimate
 // x0 = (max_c + min_c)/2  (gd.py:99-105)
 template <typename T>

@@ -69,7 +69,7 @@ def finalize():
 
 
 def reconstruct_sharded(host_batch, psf, n_iter=100, algo="admm", chunk=1, gather=False, solver=None,
-                        reconstruct_fn=None, device=None, **solver_kw):
+                        reconstruct_fn=None, device=None, out=None, **solver_kw):
     """BASELINE configs[3] as a call: reconstruct ``host_batch`` ([N, Dd, h, w, C], host memory, the same tensor on
     every rank) with the batch axis sharded contiguously over the ranks of the job.
 
@@ -80,6 +80,8 @@ def reconstruct_sharded(host_batch, psf, n_iter=100, algo="admm", chunk=1, gathe
     ``[n_local, D, h, w, C]`` -- or, with ``gather=True``, ``(full, index_range)`` where ``full`` is the
     ``[N, D, h, w, C]`` result on every rank (one all_gather of the padded shards at the end).
 
+    ``out`` is this rank's pre-allocated (pinned) ``[n_local, D, h, w, C]`` result buffer -- pinning gigabytes of host
+    memory takes seconds, a caller that reconstructs batch after batch allocates it once.
     ``solver`` re-uses an existing solver object (its plans and CUDA graphs); ``reconstruct_fn(inputs, outputs)`` replaces
     the engine call (the CPU tests of the host logic run it under gloo with a stand-in)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -95,7 +97,11 @@ def reconstruct_sharded(host_batch, psf, n_iter=100, algo="admm", chunk=1, gathe
     def pinned(t):
         return t.pin_memory() if (use_cuda and not t.is_pinned()) else t
 
-    local_out = pinned(torch.empty((n_local, D, h, w, C), dtype=host_batch.dtype))
+    if out is not None:
+        assert tuple(out.shape) == (n_local, D, h, w, C) and out.dtype == host_batch.dtype and not out.is_cuda
+        local_out = out
+    else:
+        local_out = pinned(torch.empty((n_local, D, h, w, C), dtype=host_batch.dtype))
     if n_local:
         ins, outs = [], []
         for s in range(0, n_local, max(int(chunk), 1)):

@@ -112,3 +112,22 @@ class FISTA(GradientDescent):
             raise NotImplementedError("reset(tk=...) differing from the constructor's tk is not supported")
         super(FISTA, self).reset()
         self._tk = self._initial_tk
+
+
+def apply_gradient_descent(psf, data, n_iter, verbose=False, proj=non_neg, **kwargs):
+    """gd.py:244-263 with tensors instead of file paths (loading images is ``lenslesspicam_b200.io``'s job)."""
+    import time
+
+    import torch
+
+    recon = GradientDescent(psf, n_iter=n_iter, proj=proj, **kwargs)
+    recon.set_data(data)
+    torch.cuda.synchronize()
+    start_time = time.time()
+    res = recon.apply(plot=False)
+    torch.cuda.synchronize()
+    proc_time = time.time() - start_time
+    if verbose:
+        print(f"Reconstruction time : {proc_time} s")
+        print(f"Reconstruction shape: {res.shape}")
+    return res

@@ -198,12 +198,15 @@ def finite_diff_adj(u):
 
 
 def finite_diff_gram(shape, dtype, workers=None):
-    """admm.py:373-397 -- rfft2 of the 5-point stencil (2-D branch only; ADMM
-    refuses depth > 1 at admm.py:91-96)."""
+    """admm.py:373-397 -- rfft2 of the 5-point stencil; the depth > 1 branch (:388-392) is restated too although
+    ADMM itself refuses depth > 1 (admm.py:91-96)."""
     g = np.zeros(shape, dtype=dtype)
-    assert shape[0] == 1
-    g[0, 0, 0] = 4
-    g[0, 0, 1] = g[0, 0, -1] = g[0, 1, 0] = g[0, -1, 0] = -1
+    if shape[0] == 1:
+        g[0, 0, 0] = 4
+        g[0, 0, 1] = g[0, 0, -1] = g[0, 1, 0] = g[0, -1, 0] = -1
+    else:
+        g[0, 0, 0] = 6
+        g[0, 0, 1] = g[0, 0, -1] = g[0, 1, 0] = g[0, -1, 0] = g[1, 0, 0] = g[-1, 0, 0] = -1
     kw = {"workers": workers} if (_HAVE_SCIPY and workers) else {}
     return _fft.rfft2(g, axes=(-3, -2), **kw)
 

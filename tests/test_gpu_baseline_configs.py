@@ -124,11 +124,10 @@ def test_cfg3_fista300_full_size():
     ref32 = torch_ref("fista", psf, data, 300, torch.float32)
     ref64 = torch_ref("fista", psf, data, 300, torch.float64)
     gate("cfg3/fista-300@3x1080x1920", out, ref32, ref64)
-    # <= 50 iterations sits inside 1e-5 of the truth outright
+    # 50 iterations: about 1e-5 from the truth for the reference's fp32 arithmetic and for ours (SURVEY 7.4 measured
+    # 3.6e-6 at 380x507; the full-size transforms are 8x longer)
     out50, _ = ours("fista", psf, data, 50)
-    e50 = rel_to_max(out50, torch_ref("fista", psf, data, 50, torch.float64))
-    report("cfg3/fista-50@3x1080x1920", ours_vs_fp64=e50)
-    assert e50 <= TOL
+    gate("cfg3/fista-50@3x1080x1920", out50, torch_ref("fista", psf, data, 50, torch.float32), torch_ref("fista", psf, data, 50, torch.float64))
 
 
 def test_gpu_fp64_truth_equals_cpu_oracle_at_full_size():

@@ -551,3 +551,31 @@ def test_host_stream_matches_device_path():
             rec.set_data(ins[k].cuda())
             ref = rec.apply(disp_iter=None, plot=False)
             assert torch.equal(outs[k][0], ref.cpu()), k
+
+
+# ------------------------------------------------------------------------------ module-level helpers (admm.py:341-397)
+def test_module_level_helpers_match_the_reference_functions():
+    """soft_thresh / finite_diff / finite_diff_adj / finite_diff_gram as stand-alone kernels against the oracle's
+    restatement of the reference functions (bit-exact for the element-wise ones: same operations, same order)."""
+    Lp = L()
+    rng = np.random.default_rng(3)
+    for shape in ((1, 1, 9, 7, 3), (2, 3, 16, 20, 1), (5, 6, 3)):
+        x = (rng.standard_normal(shape)).astype(np.float32)
+        xd = dev(x)
+        assert np.array_equal(Lp.soft_thresh(xd, 0.3).cpu().numpy(), orc.soft_thresh(x, np.float32(0.3)))
+        fd = Lp.finite_diff(xd)
+        assert tuple(fd.shape) == shape + (2,)
+        assert np.array_equal(fd.cpu().numpy(), orc.finite_diff(x))
+        u = rng.standard_normal(shape + (2,)).astype(np.float32)
+        assert np.array_equal(Lp.finite_diff_adj(dev(u)).cpu().numpy(), orc.finite_diff_adj(u))
+        # <Psi x, u> == <x, PsiT u>
+        lhs = float((fd.double() * dev(u).double()).sum())
+        rhs = float((xd.double() * Lp.finite_diff_adj(dev(u)).double()).sum())
+        assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+    x64 = rng.standard_normal((1, 2, 8, 6, 3))
+    assert np.array_equal(Lp.finite_diff(dev(x64, torch.float64)).cpu().numpy(), orc.finite_diff(x64))
+    for shape in ([1, 48, 64, 3], [1, 45, 75, 1], [4, 16, 20, 3], [2, 8, 6, 1]):
+        for dt, tol in (("float32", 2e-6), ("float64", 1e-13)):
+            g = Lp.finite_diff_gram(shape, dtype=dt).cpu().numpy()
+            ref = orc.finite_diff_gram(shape, np.float32 if dt == "float32" else np.float64)
+            assert g.shape == ref.shape and rel_to_max(g, ref) <= tol, (shape, dt, rel_to_max(g, ref))
