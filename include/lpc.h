@@ -79,10 +79,14 @@ extern "C" {
                                      forward(batch, psfs) builds RealFFTConvolve2D(psfs[B,...]), trainable_recon.py:347-350;
                                      eval/benchmark.py:186-190,255-259) */
 
+#define LPC_FLAG_PNP 16 /* plug-and-play plan: a caller-side denoiser replaces the prox / projection, the iteration is driven
+                           half by half through lpc_pnp_begin / lpc_pnp_finish (cuFFT engine, no CUDA graph) */
+
 /* lpc_set_option selectors */
 #define LPC_OPT_KEEP_X0 1      /* != 0: lpc_set_psf keeps the GD-family initial value (psf min/max, gd.py:99-105) of the
                                   PSF set BEFORE: UnrolledFISTA.forward(psfs) swaps the convolver only, its _image_init
                                   stays the constructor PSF's (trainable_recon.py:347-350, unrolled_fista.py:55-59) */
+#define LPC_OPT_PNP_USE_DUAL 3 /* PnP-ADMM: denoiser["use_dual"] (admm.py:127, 236-243, 266-275) */
 #define LPC_OPT_B2_PREFETCH 2  /* tuning: L2-prefetch distance (rows) of the fused spatial kernel, 0 = off */
 
 typedef struct lpc_plan_s* lpc_plan_t;
@@ -203,6 +207,17 @@ int lpc_op_soft_thresh(int device, int dtype, const void* dev_x, void* dev_out, 
 int lpc_op_finite_diff(int device, int dtype, const void* dev_x, void* dev_out, int64_t outer, int H, int W, int C, void* stream);
 int lpc_op_finite_diff_adj(int device, int dtype, const void* dev_u, void* dev_out, int64_t outer, int H, int W, int C, void* stream);
 int lpc_op_finite_diff_gram(int device, int dtype, void* dev_out, int D, int Hp, int Wp, int C, void* stream);
+
+/* ---- plug-and-play iterations (LPC_FLAG_PNP plans).  The reference lets a torch denoiser replace the U prox of ADMM
+ * (admm.py:126-133, 235-243, 266-275) and the projection of the gradient-descent family (gd.py:89-92, 136-140); the engine
+ * splits an iteration at that call:
+ *   lpc_pnp_begin   writes the denoiser's input, channels-last: ADMM [B,D,Hp,Wp,C] = U + eta/mu2 (use_dual) or V;
+ *                   GD family [B,D,h,w,C] = the stepped estimate x - alpha*grad (Nesterov: with its momentum)
+ *   lpc_pnp_finish  takes the denoised array (same shape) and completes the iteration (ADMM: X, W, image update with the
+ *                   reference's rk expression, convolve, dual updates; FISTA: momentum).
+ * One begin/finish pair = one _update (admm.py:313-329, gd.py:132-134, 183-188, 235-241). */
+int lpc_pnp_begin(lpc_plan_t plan, void* dev_denoiser_in, void* stream);
+int lpc_pnp_finish(lpc_plan_t plan, const void* dev_denoised, void* stream);
 
 /* plan-level switches, see LPC_OPT_* */
 int lpc_set_option(lpc_plan_t plan, int option, double value);

@@ -20,8 +20,8 @@ ALGO_CONV, ALGO_ADMM, ALGO_GD, ALGO_NESTEROV, ALGO_FISTA = 0, 1, 2, 3, 4
 F32, F64 = 0, 1
 NORMS = {"backward": 0, "ortho": 1, "forward": 2}
 STATE_IMAGE_EST, STATE_FORWARD, STATE_XI, STATE_RHO, STATE_ETA0, STATE_ETA1 = range(6)
-FLAG_NONE, FLAG_NO_GRAPH, FLAG_ENGINE_V1, FLAG_PSF_PER_SAMPLE = 0, 1, 4, 8
-OPT_KEEP_X0, OPT_B2_PREFETCH = 1, 2
+FLAG_NONE, FLAG_NO_GRAPH, FLAG_ENGINE_V1, FLAG_PSF_PER_SAMPLE, FLAG_PNP = 0, 1, 4, 8, 16
+OPT_KEEP_X0, OPT_B2_PREFETCH, OPT_PNP_USE_DUAL = 1, 2, 3
 
 _lock = threading.Lock()
 _lib = None
@@ -60,6 +60,8 @@ PROTOTYPES = {
     "lpc_reconstruction_error": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
     "lpc_set_image_estimate": (_i, [_vp, _vp, _vp]),
     "lpc_set_option": (_i, [_vp, _i, _d]),
+    "lpc_pnp_begin": (_i, [_vp, _vp, _vp]),
+    "lpc_pnp_finish": (_i, [_vp, _vp, _vp]),
     "lpc_op_soft_thresh": (_i, [_i, _i, _vp, _vp, ctypes.c_int64, _d, _vp]),
     "lpc_op_finite_diff": (_i, [_i, _i, _vp, _vp, ctypes.c_int64, _i, _i, _i, _vp]),
     "lpc_op_finite_diff_adj": (_i, [_i, _i, _vp, _vp, ctypes.c_int64, _i, _i, _i, _vp]),

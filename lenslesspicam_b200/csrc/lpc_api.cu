@@ -22,6 +22,7 @@
 #include "lpc_gd.cuh"
 #include "lpc_metrics.cuh"
 #include "lpc_ops.cuh"
+#include "lpc_pnp.cuh"
 #include "lpc_setup.cuh"
 #include "lpc_util.cuh"
 
@@ -146,6 +147,8 @@ struct lpc_plan_s {
     virtual int recon_error(const void*, const void*, int, int, double, void*, cudaStream_t) = 0;
     virtual int set_image_estimate(const void*, cudaStream_t) = 0;
     virtual int set_option(int, double) = 0;
+    virtual int pnp_begin(void*, cudaStream_t) = 0;
+    virtual int pnp_finish(const void*, cudaStream_t) = 0;
     virtual int bytes_per_iter(double*) = 0;
     virtual int launches_per_iter(int*, int*) = 0;
     virtual int profile(int, cudaStream_t, double*, int*) = 0;
@@ -249,6 +252,9 @@ struct Plan : lpc_plan_s {
     int gd_it = 0;                                     // FISTA schedule position (iterations since reset)
     double lip = 1.8, nmu = 0.9, tk0 = 1.0, tk = 1.0;
     bool psf_set = false, data_set = false, state_ready = false, fista_first = true;
+    // plug-and-play (lpc_pnp.cuh): plain duals xi (pnp_xi), rho (rho), eta (eta[0], first Np planes), and U, X, W
+    bool pnp = false, pnp_use_dual = false, pnp_open = false;
+    T* pnp_xi = nullptr; T* pnp_X = nullptr; T* pnp_W = nullptr; T* pnp_U = nullptr;
     bool keep_x0 = false;  // LPC_OPT_KEEP_X0: lpc_set_psf leaves the initial-value constants (psf min / max) alone
     // ---- graph cache: a few captured iteration loops, least recently used evicted (an apply() that alternates
     //      iteration counts -- disp_iter chunks, a warm-up run next to the real one -- replays instead of re-capturing)
@@ -373,6 +379,8 @@ struct Plan : lpc_plan_s {
         if ((rc = alloc(&consts, (size_t)4 * NC))) return rc;
         if ((rc = alloc(&data, (size_t)Np * h * dpitch))) return rc;  // sized for Dd == D
         int nb = Np;
+        pnp = (flags & LPC_FLAG_PNP) != 0;
+        if (pnp) flags |= LPC_FLAG_ENGINE_V1 | LPC_FLAG_NO_GRAPH;  // the split iteration runs on the cuFFT engine, host-driven
         if (algo == LPC_ALGO_ADMM && !(flags & LPC_FLAG_ENGINE_V1) && getenv("LPC_ENGINE_V1") == nullptr) {
             if ((rc = init_v2())) return rc;
         }
@@ -384,6 +392,12 @@ struct Plan : lpc_plan_s {
             if ((rc = alloc(&eta[0], (size_t)2 * Np * plane))) return rc;
             if ((rc = alloc(&eta[1], (size_t)2 * Np * plane))) return rc;
             if ((rc = alloc(&Rn, (size_t)PQ * splane))) return rc;
+            if (pnp) {
+                if ((rc = alloc(&pnp_xi, (size_t)Np * plane))) return rc;
+                if ((rc = alloc(&pnp_X, (size_t)Np * plane))) return rc;
+                if ((rc = alloc(&pnp_W, (size_t)Np * plane))) return rc;
+                if ((rc = alloc(&pnp_U, (size_t)Np * plane))) return rc;
+            }
         } else {
             if (algo >= LPC_ALGO_GD && !(flags & LPC_FLAG_ENGINE_V1) && getenv("LPC_ENGINE_V1") == nullptr) {
                 if ((rc = init_gd2())) return rc;
@@ -1023,6 +1037,10 @@ struct Plan : lpc_plan_s {
             LPC_CK(cudaMemsetAsync(rho, 0, (size_t)Np * plane * sizeof(T), st));
             LPC_CK(cudaMemsetAsync(eta[0], 0, (size_t)2 * Np * plane * sizeof(T), st));
             eta_cur = 0;
+            if (pnp) {  // plain duals and U, X, W all start at zero (admm.py:161-183)
+                for (T* a : {pnp_xi, pnp_X, pnp_W, pnp_U}) LPC_CK(cudaMemsetAsync(a, 0, (size_t)Np * plane * sizeof(T), st));
+                pnp_open = false;
+            }
             { double m[4]; admm_params(0, m); pm1 = m[0]; pm2 = m[1]; pm3 = m[2]; }
             if (v2) {
                 LPC_CK(cudaMemsetAsync(Tin, 0, (size_t)Np * fk.NT * Hp * 2 * LPC_NCT * sizeof(Cplx), st));
@@ -1044,10 +1062,12 @@ struct Plan : lpc_plan_s {
                 LPC_CF(FftTraits<T>::fwd(fwd1, VH, sp));
                 if ((rc = spec_mul(sp, Np, 0, st))) return rc;
                 LPC_CF(FftTraits<T>::inv(inv1, sp, VH + (int64_t)Np * plane));
-                dim3 grid((Wp + 127) / 128, Hp, Np);
-                k_admm_warm_start<T><<<grid, 128, 0, st>>>(admm_k(), VH, VH + (int64_t)Np * plane, AX + (int64_t)Np * plane,
-                                                          rho, eta[0]);
-                LPC_KCHECK();
+                if (!pnp) {
+                    dim3 grid((Wp + 127) / 128, Hp, Np);
+                    k_admm_warm_start<T><<<grid, 128, 0, st>>>(admm_k(), VH, VH + (int64_t)Np * plane, AX + (int64_t)Np * plane,
+                                                              rho, eta[0]);
+                    LPC_KCHECK();
+                }
                 if (v2) {  // row spectra of (V, HV)/Wp into Tin
                     if ((rc = launch_rows_fft(st, (T)(0.5 / (double)Wp)))) return rc;
                     vh_valid = true;
@@ -1076,6 +1096,7 @@ struct Plan : lpc_plan_s {
             gd_it = 0;
             tk = tk0;            // gd.py:227-233
             fista_first = true;  // xk aliases x right after reset (gd.py:233)
+            pnp_open = false;
         }
         state_ready = true;
         return LPC_OK;
@@ -1287,8 +1308,78 @@ struct Plan : lpc_plan_s {
         return rc;
     }
 
+    // ---------------------------------------------------------------- plug-and-play halves (lpc_pnp.cuh)
+    int pnp_begin(void* dev_out, cudaStream_t st) override {
+        if (!pnp) return fail(LPC_ESTATE, "pnp_begin", "not a plug-and-play plan (LPC_FLAG_PNP)");
+        if (!psf_set || !data_set || !state_ready) return fail(LPC_ESTATE, "pnp_begin", "PSF, data and reset first");
+        if (pnp_open) return fail(LPC_ESTATE, "pnp_begin", "the previous iteration was not finished");
+        if (!dev_out) return fail(LPC_EINVAL, "pnp_begin", "null output");
+        if (algo == LPC_ALGO_ADMM) {
+            dim3 grid((Wp + 127) / 128, Hp, Np);
+            k_pnp_admm_pre<T><<<grid, 128, 0, st>>>(admm_k(), VH, pnp_U, eta[0], (T*)dev_out, pnp_use_dual ? 1 : 0);
+            LPC_KCHECK();
+        } else {
+            // gradient (gd.py:128-130) on the cuFFT engine, then the step up to the projection
+            const GdK k = gd_k();
+            int rc;
+            LPC_CF(cufftSetStream(fwd, st));
+            LPC_CF(cufftSetStream(inv, st));
+            LPC_CF(FftTraits<T>::fwd(fwd, xpad, spec));
+            if ((rc = spec_mul(spec, Np, 0, st))) return rc;
+            LPC_CF(FftTraits<T>::inv(inv, spec, rpad));
+            dim3 grid((w + 127) / 128, h, Np);
+            k_gd_residual<T><<<grid, 128, 0, st>>>(k, rpad, data, dpad);
+            LPC_CF(FftTraits<T>::fwd(fwd, dpad, spec));
+            if ((rc = spec_mul(spec, Np, 1, st))) return rc;
+            LPC_CF(FftTraits<T>::inv(inv, spec, rpad));
+            T* momp = mom ? mom : xpad;  // plain GD has no momentum buffer (never dereferenced for it)
+            k_pnp_gd_step<T><<<grid, 128, 0, st>>>(k, algo, rpad, consts, xpad, momp, (T)nmu, fista_first ? 1 : 0, (T*)dev_out);
+            LPC_KCHECK();
+        }
+        pnp_open = true;
+        return LPC_OK;
+    }
+    int pnp_finish(const void* dev_den, cudaStream_t st) override {
+        if (!pnp) return fail(LPC_ESTATE, "pnp_finish", "not a plug-and-play plan (LPC_FLAG_PNP)");
+        if (!pnp_open) return fail(LPC_ESTATE, "pnp_finish", "lpc_pnp_begin first");
+        if (!dev_den) return fail(LPC_EINVAL, "pnp_finish", "null input");
+        pnp_open = false;
+        if (algo == LPC_ALGO_ADMM) {
+            const AdmmK<T> k = admm_k();
+            T* V = VH; T* HV = VH + (int64_t)Np * plane;
+            T* a = AX; T* nbq = AX + (int64_t)Np * plane;
+            dim3 grid((Wp + 127) / 128, Hp, Np);
+            k_pnp_admm_mid<T><<<grid, 128, 0, st>>>(k, (const T*)dev_den, V, HV, data, pnp_xi, rho, eta[0], pnp_U, pnp_X, pnp_W, a, nbq,
+                                                     pnp_use_dual ? 1 : 0);
+            LPC_KCHECK();
+            LPC_CF(cufftSetStream(fwd, st));
+            LPC_CF(cufftSetStream(inv, st));
+            LPC_CF(FftTraits<T>::fwd(fwd, AX, spec));
+            dim3 g2((unsigned)((splane + 255) / 256), Np);
+            k_admm_spectral<T><<<g2, 256, 0, st>>>(spec, Hc, Rn, Sy, Sx, Np, PQ, Hp, Nh);
+            LPC_KCHECK();
+            LPC_CF(FftTraits<T>::inv(inv, spec, VH));
+            k_pnp_admm_post<T><<<grid, 128, 0, st>>>(k, V, HV, pnp_X, pnp_W, pnp_U, pnp_xi, rho, eta[0], pnp_use_dual ? 1 : 0);
+            LPC_KCHECK();
+        } else {
+            T beta = T(0);
+            if (algo == LPC_ALGO_FISTA) {
+                const double tn = (1.0 + std::sqrt(1.0 + 4.0 * tk * tk)) / 2.0;  // gd.py:238
+                beta = (T)((tk - 1.0) / tn);
+                tk = tn;
+                fista_first = false;
+            }
+            dim3 grid((w + 127) / 128, h, Np);
+            T* momp = mom ? mom : xpad;
+            k_pnp_gd_finish<T><<<grid, 128, 0, st>>>(gd_k(), algo, (const T*)dev_den, xpad, momp, beta);
+            LPC_KCHECK();
+        }
+        return LPC_OK;
+    }
+
     int run(int n_iter, cudaStream_t st) override {
         if (algo == LPC_ALGO_CONV) return fail(LPC_ESTATE, "run", "convolver plans do not iterate");
+        if (pnp) return fail(LPC_ESTATE, "run", "plug-and-play plans iterate through lpc_pnp_begin / lpc_pnp_finish");
         if (!psf_set || !data_set) return fail(LPC_ESTATE, "run", "PSF and data must be set first");
         if (!state_ready) return fail(LPC_ESTATE, "run", "call lpc_reset first");
         if (n_iter < 0) return fail(LPC_EINVAL, "run", "n_iter < 0");
@@ -1506,6 +1597,7 @@ struct Plan : lpc_plan_s {
     int set_option(int option, double value) override {
         switch (option) {
             case LPC_OPT_KEEP_X0: keep_x0 = value != 0.0; return LPC_OK;
+            case LPC_OPT_PNP_USE_DUAL: pnp_use_dual = value != 0.0; return LPC_OK;
             case LPC_OPT_B2_PREFETCH: b2_prefetch = (int)value; drop_graph(); return LPC_OK;
             default: return fail(LPC_EINVAL, "set_option", "unknown option");
         }
@@ -1691,6 +1783,14 @@ int lpc_reconstruction_error(lpc_plan_t plan, const void* dev_prediction, const 
 int lpc_set_image_estimate(lpc_plan_t plan, const void* dev_est, void* stream) {
     LPC_NEED(plan);
     return plan->set_image_estimate(dev_est, (cudaStream_t)stream);
+}
+int lpc_pnp_begin(lpc_plan_t plan, void* dev_denoiser_in, void* stream) {
+    LPC_NEED(plan);
+    return plan->pnp_begin(dev_denoiser_in, (cudaStream_t)stream);
+}
+int lpc_pnp_finish(lpc_plan_t plan, const void* dev_denoised, void* stream) {
+    LPC_NEED(plan);
+    return plan->pnp_finish(dev_denoised, (cudaStream_t)stream);
 }
 int lpc_set_option(lpc_plan_t plan, int option, double value) {
     LPC_NEED(plan);

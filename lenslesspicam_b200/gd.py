@@ -42,9 +42,11 @@ class GradientDescent(ReconstructionAlgorithm):
 
     def __init__(self, psf, dtype=None, proj=non_neg, lip_fact=1.8, **kwargs):
         assert callable(proj)
-        if proj is not non_neg and getattr(proj, "__name__", "") != "non_neg":
-            raise NotImplementedError("only the non-negativity projection is fused in the B200 engine")
         self._proj = proj
+        if proj is not non_neg and getattr(proj, "__name__", "") != "non_neg" and kwargs.get("denoiser") is None:
+            # only the non-negativity projection is fused into the update kernels; any other callable runs between the
+            # two halves of the split iteration, like a plug-and-play denoiser (csrc/lpc_pnp.cuh)
+            kwargs["denoiser"] = {"network": (lambda x, _noise_level, _p=proj: _p(x)), "noise_level": None}
         self._lip_fact = lip_fact
         kwargs.setdefault("pad", True)
         if not kwargs["pad"]:

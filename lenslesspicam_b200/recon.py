@@ -67,9 +67,24 @@ class ReconstructionAlgorithm(abc.ABC):
         # recon.py:255-256
         assert len(psf.shape) == 4, "PSF must be 4D: (depth, height, width, channels)."
         assert psf.shape[3] == 3 or psf.shape[3] == 1, "PSF must either be rgb (3) or grayscale (1)"
-        if denoiser is not None:
-            raise NotImplementedError("plug-and-play denoisers are not fused in the B200 engine (SURVEY 8f.4)")
+        # recon.py:308-322: plug-and-play.  The reference only knows the name "DruNet" (weights fetched from the hub);
+        # here ``denoiser["network"]`` may also be any callable ``f(image, noise_level) -> image`` on torch CUDA tensors.
+        # The iteration is then split around the call (lpc_pnp_begin / lpc_pnp_finish, csrc/lpc_pnp.cuh).
         self._denoiser = None
+        self._denoiser_noise_level = None
+        self._denoiser_use_dual = False
+        if denoiser is not None:
+            assert "network" in denoiser.keys()
+            assert "noise_level" in denoiser.keys()
+            net = denoiser["network"]
+            if callable(net):
+                self._denoiser = net
+            elif net == "DruNet":
+                self._denoiser = _load_drunet_function(psf.device)
+            else:
+                raise NotImplementedError(f"Unsupported denoiser: {net}")
+            self._denoiser_noise_level = denoiser["noise_level"]
+            self._denoiser_use_dual = bool(denoiser.get("use_dual", False))
         self._n_iter = n_iter
         self._npix = np.prod(psf.shape)
         self._psf_shape = np.array(psf.shape)
@@ -114,6 +129,8 @@ class ReconstructionAlgorithm(abc.ABC):
         self._flags = _lib.FLAG_NO_GRAPH if kwargs.get("no_graph", False) else _lib.FLAG_NONE
         if kwargs.get("engine", None) == "v1":  # K1/K2 + cuFFT instead of the fused own-FFT engine (A/B, bisecting)
             self._flags |= _lib.FLAG_ENGINE_V1
+        if self._denoiser is not None:
+            self._flags |= _lib.FLAG_PNP
 
         if initial_est is not None:
             self._set_initial_estimate(initial_est)
@@ -159,7 +176,9 @@ class ReconstructionAlgorithm(abc.ABC):
                 )
             )
             self._plans[key] = plan
-            if (self._dtype == torch.float32 and lib.lpc_engine_version(plan) != 2 and not (self._flags & _lib.FLAG_ENGINE_V1)
+            if self._denoiser is not None:
+                _lib.check(lib.lpc_set_option(plan, _lib.OPT_PNP_USE_DUAL, 1.0 if self._denoiser_use_dual else 0.0), plan)
+            if (self._dtype == torch.float32 and lib.lpc_engine_version(plan) != 2 and not (self._flags & (_lib.FLAG_ENGINE_V1 | _lib.FLAG_PNP))
                     and not ReconstructionAlgorithm._warned_v1):
                 ReconstructionAlgorithm._warned_v1 = True
                 _, Hp, Wp, _ = self._padded_shape
@@ -351,14 +370,36 @@ class ReconstructionAlgorithm(abc.ABC):
 
     def _update(self, iter):
         """One iteration (recon.py:338-343); ``apply`` runs all of them in one call instead."""
+        self._ensure_plan()
+        self._run(1)
+
+    def _run(self, n_iter):
+        """``n_iter`` iterations on the current plan: one captured CUDA graph, or -- plug-and-play -- a host loop of
+        begin / denoiser / finish (admm.py:235-243,266-275,313-329; gd.py:132-140)."""
         lib = _lib.load()
-        plan = self._ensure_plan()
-        with self._stream as st:
-            _lib.check(lib.lpc_run(plan, 1, st), plan)
+        plan = self._plan
+        if self._denoiser is None:
+            with self._stream as st:
+                _lib.check(lib.lpc_run(plan, int(n_iter), st), plan)
+            return
+        D, Hp, Wp, C = self._padded_shape
+        shape = (self._B, D, Hp, Wp, C) if not self._pad else (self._B,) + tuple(int(v) for v in self._psf.shape)
+        for _ in range(int(n_iter)):
+            buf = torch.empty(shape, dtype=self._dtype, device=self._device)
+            with self._stream as st:
+                _lib.check(lib.lpc_pnp_begin(plan, buf.data_ptr(), st), plan)
+            den = self._denoiser(buf, self._denoiser_noise_level)
+            den = den.to(device=self._device, dtype=self._dtype).contiguous()
+            assert tuple(den.shape) == tuple(shape), "the denoiser must return an array of its input's shape"
+            with self._stream as st:
+                _lib.check(lib.lpc_pnp_finish(plan, den.data_ptr(), st), plan)
 
     def _form_image(self):
         """admm.py:331-338 / gd.py:136-140 -> fresh [B, D, h, w, C] tensor."""
         D, h, w, C = (int(v) for v in self._psf.shape)
+        if self._denoiser is not None and self._pad:
+            # gd.py:136-140: with a denoiser the projection IS the denoiser, applied to the current iterate
+            return self._denoiser(self._image_est, self._denoiser_noise_level)
         out = torch.empty((self._B, D, h, w, C), dtype=self._dtype, device=self._device)
         lib = _lib.load()
         plan = self._ensure_plan()
@@ -405,8 +446,7 @@ class ReconstructionAlgorithm(abc.ABC):
             done = 0
             while done < n_iter:
                 step = min(disp_iter - (done % disp_iter), n_iter - done)
-                with self._stream as st:
-                    _lib.check(lib.lpc_run(self._plan, int(step), st), self._plan)
+                self._run(step)
                 done += step
                 if done % disp_iter == 0:
                     self._progress()
@@ -420,8 +460,7 @@ class ReconstructionAlgorithm(abc.ABC):
                         plt.pause(plot_pause)
         else:
             ax = None
-            with self._stream as st:
-                _lib.check(lib.lpc_run(self._plan, int(n_iter), st), self._plan)
+            self._run(n_iter)
 
         img = self._form_image()
         final_im = img[0] if self._B == 1 else img
@@ -575,6 +614,20 @@ class ReconstructionAlgorithm(abc.ABC):
         v = ctypes.c_double()
         _lib.check(lib.lpc_bytes_per_iter(self._ensure_plan(), ctypes.byref(v)), self._plan)
         return v.value
+
+
+def _load_drunet_function(device):
+    """recon.py:317-319: ``denoiser["network"] == "DruNet"``.  The weights come from the reference's model hub
+    (lensless.recon.utils.load_drunet); without the reference package and network access this raises."""
+    try:
+        from lensless.recon.utils import get_drunet_function_v2, load_drunet
+    except Exception as e:  # pragma: no cover
+        raise NotImplementedError(
+            'denoiser["network"] == "DruNet" needs the reference package (lensless.recon.utils.load_drunet) and its '
+            "downloaded weights; pass a callable f(image, noise_level) instead"
+        ) from e
+    model = load_drunet(requires_grad=False).to(device)
+    return get_drunet_function_v2(model, mode="inference")
 
 
 def _import_plotting():

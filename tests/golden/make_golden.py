@@ -182,6 +182,55 @@ def make_bundled_large(lensless, torch):
               {k: float(np.abs(v).max()) for k, v in store.items() if k.startswith(("admm", "fista"))})
 
 
+def standin_denoiser(x, noise_level):
+    """deterministic stand-in for DruNet in the plug-and-play goldens / tests: a 5-point periodic blur blended in by
+    ``noise_level``, clamped at zero; shape-preserving on [..., H, W, C] tensors"""
+    import torch
+
+    blur = (x + torch.roll(x, 1, -3) + torch.roll(x, -1, -3) + torch.roll(x, 1, -2) + torch.roll(x, -1, -2)) / 5.0
+    return torch.clamp((1.0 - noise_level) * x + noise_level * blur, min=0.0)
+
+
+def make_pnp(lensless, torch):
+    """``pnp.npz``: the reference's plug-and-play branches (admm.py:126-133,235-243,266-275,302-329; gd.py:89-92,136-140)
+    with a stand-in denoiser.  The reference constructor only accepts the name "DruNet" (weights from the hub), so the
+    objects are built without a denoiser and then put into exactly the state the constructor's PnP branch creates
+    (admm.py:126-135: _denoiser, _denoiser_noise_level, _denoiser_use_dual, _proj = denoiser, _PsiT = identity, reset();
+    gd.py:89-92: _proj = denoiser); every iteration after that is the reference's own code."""
+    psf, data = synth(24, 32, 3, 31)
+    nl = 0.3
+    rng = np.random.default_rng(32)
+    init = (rng.random((1, 1, 48, 64, 3)) * 0.1).astype(np.float32)  # padded-shape warm start: with use_dual the
+    # reference's rk has no data term (admm.py:266-275), a zero start would stay zero
+    store = {"psf": psf, "data": data, "noise_level": np.float64(nl), "init": init}
+    for use_dual in (True, False):
+        for tag, conv in (("t32", np.float32), ("t64", np.float64)):
+            rec = lensless.ADMM(torch.from_numpy(psf.astype(conv)), dtype="float32" if conv is np.float32 else "float64",
+                                initial_est=torch.from_numpy(init.astype(conv).copy()) if use_dual else None)
+            rec._denoiser = standin_denoiser
+            rec._denoiser_noise_level = nl
+            rec._denoiser_use_dual = use_dual
+            rec._proj = rec._denoiser
+            rec._PsiT = lambda x: x
+            rec.reset()
+            rec.set_data(torch.from_numpy(data.astype(conv)))
+            store[f"admm_dual{int(use_dual)}_{tag}_8"] = rec.apply(n_iter=8, disp_iter=None, plot=False).numpy().copy()
+    for key, cls in (("gd", lensless.GradientDescent), ("nesterov", lensless.NesterovGradientDescent), ("fista", lensless.FISTA)):
+        for tag, conv in (("t32", np.float32), ("t64", np.float64)):
+            rec = cls(torch.from_numpy(psf.astype(conv)), dtype="float32" if conv is np.float32 else "float64")
+            rec._denoiser = standin_denoiser
+            rec._denoiser_noise_level = nl
+            rec._proj = rec._denoiser
+            rec.set_data(torch.from_numpy(data.astype(conv)))
+            store[f"{key}_{tag}_8"] = rec.apply(n_iter=8, disp_iter=None, plot=False).numpy().copy()
+    # a custom projection (gd.py:84-86): clamp into [0, 0.05]
+    rec = lensless.FISTA(torch.from_numpy(psf), proj=lambda x: torch.clamp(x, 0.0, 0.05))
+    rec.set_data(torch.from_numpy(data))
+    store["fista_boxproj_t32_8"] = rec.apply(n_iter=8, disp_iter=None, plot=False).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "pnp.npz"), **store)
+    print("wrote pnp.npz", {k: float(np.abs(v).max()) for k, v in store.items() if "_t32_" in k})
+
+
 def make_recon_error(lensless, torch):
     """``recon_error.npz``: reconstruction_error (recon.py:607-653) of ADMM (pad=False branch) and FISTA (pad=True
     branch) on a small case, normalised and raw, default arguments and explicit (prediction, lensless, psfs)."""
@@ -227,6 +276,8 @@ def main():
         return make_bundled_large(lensless, torch)
     if "--only-recon-error" in sys.argv:
         return make_recon_error(lensless, torch)
+    if "--only-pnp" in sys.argv:
+        return make_pnp(lensless, torch)
 
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -346,6 +397,7 @@ def main():
     print("wrote bundled_ds16.npz", psf.shape, data.shape)
     make_bundled_large(lensless, torch)
     make_recon_error(lensless, torch)
+    make_pnp(lensless, torch)
 
 
 if __name__ == "__main__":

@@ -579,3 +579,46 @@ def test_module_level_helpers_match_the_reference_functions():
             g = Lp.finite_diff_gram(shape, dtype=dt).cpu().numpy()
             ref = orc.finite_diff_gram(shape, np.float32 if dt == "float32" else np.float64)
             assert g.shape == ref.shape and rel_to_max(g, ref) <= tol, (shape, dt, rel_to_max(g, ref))
+
+
+# ------------------------------------------------------------------------------ plug-and-play
+def standin_denoiser(x, noise_level):
+    """the stand-in of tests/golden/make_golden.py::standin_denoiser (same torch operations)"""
+    blur = (x + torch.roll(x, 1, -3) + torch.roll(x, -1, -3) + torch.roll(x, 1, -2) + torch.roll(x, -1, -2)) / 5.0
+    return torch.clamp((1.0 - noise_level) * x + noise_level * blur, min=0.0)
+
+
+def test_plug_and_play_matches_reference():
+    """A torch denoiser between the two halves of every iteration (admm.py:126-133,235-243,266-275,302-329;
+    gd.py:89-92,136-140) against the reference's own PnP branches run with the same stand-in denoiser, including the
+    reference's operator-precedence quirk in the PnP image update and the first-iteration FISTA aliasing."""
+    g = load_golden("pnp")
+    nl = float(g["noise_level"])
+    for use_dual in (True, False):
+        den = {"network": standin_denoiser, "noise_level": nl, "use_dual": use_dual}
+        kw = {"initial_est": dev(g["init"])} if use_dual else {}
+        rec = L().ADMM(dev(g["psf"]), denoiser=den, **kw)
+        rec.set_data(dev(g["data"]))
+        out = rec.apply(n_iter=8, disp_iter=None, plot=False).cpu().numpy()
+        ref = g[f"admm_dual{int(use_dual)}_t32_8"]
+        assert out.shape == ref.shape and np.abs(ref).max() > 0
+        assert rel_to_max(out, ref) <= TOL, (use_dual, rel_to_max(out, ref))
+        assert rel_to_max(out, g[f"admm_dual{int(use_dual)}_t64_8"]) <= TOL
+        # iteration by iteration == one call
+        rec2 = L().ADMM(dev(g["psf"]), denoiser=den, **kw)
+        rec2.set_data(dev(g["data"]))
+        rec2.apply(n_iter=3, disp_iter=None, plot=False)
+        again = rec2.apply(n_iter=5, disp_iter=None, plot=False, reset=False)
+        assert rel_to_max(again.cpu().numpy(), out) <= 1e-6
+    for algo in ("gd", "nesterov", "fista"):
+        rec = getattr(L(), ALGOS[algo])(dev(g["psf"]), denoiser={"network": standin_denoiser, "noise_level": nl})
+        rec.set_data(dev(g["data"]))
+        out = rec.apply(n_iter=8, disp_iter=None, plot=False).cpu().numpy()
+        assert rel_to_max(out, g[f"{algo}_t32_8"]) <= TOL, (algo, rel_to_max(out, g[f"{algo}_t32_8"]))
+    # a custom projection callable runs through the same split (gd.py:84-86)
+    rec = L().FISTA(dev(g["psf"]), proj=lambda x: torch.clamp(x, 0.0, 0.05))
+    rec.set_data(dev(g["data"]))
+    out = rec.apply(n_iter=8, disp_iter=None, plot=False).cpu().numpy()
+    assert rel_to_max(out, g["fista_boxproj_t32_8"]) <= TOL
+    with pytest.raises(NotImplementedError):
+        L().ADMM(dev(g["psf"]), denoiser={"network": "NoSuchNet", "noise_level": 1})
