@@ -219,6 +219,28 @@ int lpc_op_finite_diff_gram(int device, int dtype, void* dev_out, int D, int Hp,
 int lpc_pnp_begin(lpc_plan_t plan, void* dev_denoiser_in, void* stream);
 int lpc_pnp_finish(lpc_plan_t plan, const void* dev_denoised, void* stream);
 
+/* ---- the input side on the GPU: lensless/utils/io.py load_psf (:210-388) and load_image (:20-207) on a
+ * decoded sensor frame resident in device memory (raw uint8 / uint16 [H,W,C], C in {1,3}; PNG decode stays on the
+ * host).  float32 channels-last outputs [1, out_h, out_w, C] that feed lpc_set_psf / lpc_set_data directly.
+ *   lpc_io_load_psf   BGR->RGB + flips, background = per-channel mean of the [bg_pix0, bg_pix1)^2 corner (skipped when
+ *                     bg_pix1 <= bg_pix0), subtract + clip, antialiased resize (torchvision Resize(antialias=True),
+ *                     utils/image.py:28-67), optional channel sum (single_psf), L2 normalisation; dev_bg_out[C] receives
+ *                     the background level / max_val (io.py:376) for the measurement's subtraction
+ *   lpc_io_load_image BGR->RGB + flips, subtract dev_bg[C] * max_val (io.py:164-171; NULL: none) + clip, resize,
+ *                     normalize != 0: divide by the maximum (io.py:196-197)
+ *   lpc_io_rgb2gray   utils/image.py:158-206 (numpy branch): [npix,3] -> [npix] with weights 0.299/0.587/0.114 */
+#define LPC_IO_BGR 1        /* raw channel order is BGR (cv2.imread), io.py:151-152 */
+#define LPC_IO_FLIP_UD 2
+#define LPC_IO_FLIP_LR 4
+#define LPC_IO_SINGLE_PSF 8 /* io.py:363-368 */
+#define LPC_IO_NORMALIZE_FIRST 16 /* lpc_io_load_image: divide by the maximum BEFORE the resize -- load_data normalises the
+                                     full-resolution measurement and only then resizes it to the PSF's shape (io.py:509-513,545-547) */
+int lpc_io_load_psf(int device, int raw_bits, const void* dev_raw, int H, int W, int C, int flags, int bg_pix0, int bg_pix1,
+                    int out_h, int out_w, void* dev_psf_out, void* dev_bg_out, void* stream);
+int lpc_io_load_image(int device, int raw_bits, const void* dev_raw, int H, int W, int C, int flags, const void* dev_bg,
+                      int out_h, int out_w, int normalize, void* dev_out, void* stream);
+int lpc_io_rgb2gray(int device, const void* dev_rgb, void* dev_gray, int64_t npix, void* stream);
+
 /* plan-level switches, see LPC_OPT_* */
 int lpc_set_option(lpc_plan_t plan, int option, double value);
 

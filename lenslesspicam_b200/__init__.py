@@ -22,6 +22,7 @@ _EXPORTS = {
     "FISTA": "gd", "GradientDescent": "gd", "GradientDescentUpdate": "gd", "NesterovGradientDescent": "gd",
     "non_neg": "gd", "apply_gradient_descent": "gd",
     "UnrolledADMM": "unrolled", "UnrolledFISTA": "unrolled",
+    "load_data": "io", "load_psf": "io", "load_image": "io", "rgb2gray": "io",
 }
 __all__ = sorted(_EXPORTS)
 

@@ -60,6 +60,9 @@ PROTOTYPES = {
     "lpc_reconstruction_error": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
     "lpc_set_image_estimate": (_i, [_vp, _vp, _vp]),
     "lpc_set_option": (_i, [_vp, _i, _d]),
+    "lpc_io_load_psf": (_i, [_i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lpc_io_load_image": (_i, [_i, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "lpc_io_rgb2gray": (_i, [_i, _vp, _vp, ctypes.c_int64, _vp]),
     "lpc_pnp_begin": (_i, [_vp, _vp, _vp]),
     "lpc_pnp_finish": (_i, [_vp, _vp, _vp]),
     "lpc_op_soft_thresh": (_i, [_i, _i, _vp, _vp, ctypes.c_int64, _d, _vp]),

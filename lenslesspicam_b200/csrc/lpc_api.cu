@@ -21,6 +21,7 @@
 #include "lpc_fused_tma.cuh"
 #include "lpc_gd.cuh"
 #include "lpc_metrics.cuh"
+#include "lpc_io.cuh"
 #include "lpc_ops.cuh"
 #include "lpc_pnp.cuh"
 #include "lpc_setup.cuh"
@@ -1639,6 +1640,134 @@ struct Plan : lpc_plan_s {
 
 }  // namespace
 
+// ---- input side on the GPU (lpc_io.cuh; io.py:20-207, 210-388)
+namespace {
+// weights of one antialiased axis (ATen UpSampleKernel.cpp: _compute_indices_min_size_weights_aa with the triangle
+// filter, float arithmetic as for float32 images); returns max_w
+int aa_axis_weights(int n_in, int n_out, std::vector<int2>* idx, std::vector<float>* wts) {
+    const float scale = (float)n_in / (float)n_out;  // area_pixel_compute_scale, align_corners = false, no scale factor
+    const float support = (scale >= 1.0f) ? 1.0f * scale : 1.0f;  // interp_size 2 -> * 0.5 * 2
+    const int max_w = (int)std::ceil(support) * 2 + 1;
+    idx->assign(n_out, int2{0, 0});
+    wts->assign((size_t)n_out * max_w, 0.0f);
+    const float invscale = (scale >= 1.0f) ? 1.0f / scale : 1.0f;
+    for (int i = 0; i < n_out; ++i) {
+        const float center = scale * (i + 0.5f);
+        int64_t xmin = (int64_t)(center - support + 0.5f);
+        if (xmin < 0) xmin = 0;
+        int64_t xmax = (int64_t)(center + support + 0.5f);
+        if (xmax > n_in) xmax = n_in;
+        const int xsize = (int)(xmax - xmin);
+        float total = 0.0f;
+        float* w = wts->data() + (size_t)i * max_w;
+        for (int j = 0; j < xsize; ++j) {
+            float x = ((float)(j + xmin) - center + 0.5f) * invscale;
+            x = std::fabs(x);
+            w[j] = x < 1.0f ? 1.0f - x : 0.0f;
+            total += w[j];
+        }
+        if (total != 0.0f) for (int j = 0; j < xsize; ++j) w[j] /= total;
+        (*idx)[i] = int2{(int)xmin, xsize};
+    }
+    return max_w;
+}
+struct IoScratch {  // stream-ordered scratch, freed on the same stream
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit IoScratch(cudaStream_t s) : st(s) {}
+    template <typename U> U* get(size_t n) {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, n * sizeof(U) + 16, st) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return (U*)p;
+    }
+    ~IoScratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+};
+// [D,H,W,C] -> [D,h,w,C]: width pass then height pass (ATen separable_upsample_generic_Nd_kernel_impl)
+int io_resize(IoScratch& sc, const float* in, float* out, int D, int H, int W, int C, int h, int w, cudaStream_t st) {
+    const float* cur = in;
+    int curW = W;
+    if (w != W) {
+        std::vector<int2> idx; std::vector<float> wts;
+        const int mw = aa_axis_weights(W, w, &idx, &wts);
+        int2* didx = sc.get<int2>(idx.size()); float* dw = sc.get<float>(wts.size());
+        float* tmp = (h == H) ? out : sc.get<float>((size_t)D * H * w * C);
+        if (!didx || !dw || !tmp) return LPC_ENOMEM;
+        cudaMemcpyAsync(didx, idx.data(), idx.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dw, wts.data(), wts.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);  // idx / wts are pageable host temporaries
+        const int64_t n = (int64_t)D * H * w * C;
+        k_io_resize_axis<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 32), 256, 0, st>>>(cur, tmp, (int64_t)D * H, W, w, C, didx, dw, mw);
+        cur = tmp; curW = w;
+    }
+    if (h != H) {
+        std::vector<int2> idx; std::vector<float> wts;
+        const int mw = aa_axis_weights(H, h, &idx, &wts);
+        int2* didx = sc.get<int2>(idx.size()); float* dw = sc.get<float>(wts.size());
+        if (!didx || !dw) return LPC_ENOMEM;
+        cudaMemcpyAsync(didx, idx.data(), idx.size() * sizeof(int2), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dw, wts.data(), wts.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+        const int64_t n = (int64_t)D * h * curW * C;
+        k_io_resize_axis<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 32), 256, 0, st>>>(cur, out, D, H, h, (int64_t)curW * C, didx, dw, mw);
+        cur = out;
+    }
+    if (cur != out) cudaMemcpyAsync(out, cur, (size_t)D * h * w * C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    return cudaGetLastError() == cudaSuccess ? LPC_OK : LPC_ECUDA;
+}
+template <typename RAW>
+int io_load(int is_psf, const RAW* raw, int H, int W, int C, int flags, int bg0, int bg1, const float* dev_bg_in, int out_h, int out_w,
+            int normalize, float* dev_out, float* dev_bg_out, cudaStream_t st) {
+    IoScratch sc(st);
+    const int64_t n = (int64_t)H * W * C;
+    float* f = sc.get<float>((size_t)n);
+    unsigned int* rmax = sc.get<unsigned int>(4);
+    float* maxval = sc.get<float>(4);
+    double* sumsq = sc.get<double>(2);
+    if (!f || !rmax || !maxval || !sumsq) return LPC_ENOMEM;
+    cudaMemsetAsync(rmax, 0, 16, st);
+    cudaMemsetAsync(sumsq, 0, 16, st);
+    const unsigned nb = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 32);
+    k_io_raw_to_float<RAW><<<nb, 256, 0, st>>>(raw, f, H, W, C, (flags & LPC_IO_BGR) ? 1 : 0, (flags & LPC_IO_FLIP_UD) ? 1 : 0,
+                                              (flags & LPC_IO_FLIP_LR) ? 1 : 0, rmax);
+    k_io_max_val<<<1, 32, 0, st>>>(rmax, maxval);
+    if (is_psf) {
+        if (bg1 > bg0) {  // io.py:343-357
+            if (bg1 > H || bg1 > W || bg0 < 0 || !dev_bg_out) return LPC_EINVAL;
+            k_io_region_mean<<<C, 256, 0, st>>>(f, 1, H, W, C, bg0, bg1, dev_bg_out);
+            k_io_sub_clip<<<nb, 256, 0, st>>>(f, n, C, dev_bg_out, nullptr);
+        }
+    } else if (dev_bg_in) {  // io.py:164-171: bg is the PSF's normalised background level, scaled back to counts
+        k_io_sub_clip<<<nb, 256, 0, st>>>(f, n, C, dev_bg_in, maxval);
+    }
+    unsigned int* vmax = rmax + 1;
+    const bool norm_first = !is_psf && normalize && (flags & LPC_IO_NORMALIZE_FIRST);
+    if (norm_first) {  // load_data normalises the full-resolution measurement BEFORE resizing it to the PSF's shape (io.py:509-513,545-547)
+        k_io_reduce<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(f, n, sumsq, vmax);
+        k_io_normalize<<<nb, 256, 0, st>>>(f, n, sumsq, vmax, 1);
+    }
+    int Cc = C;
+    float* src = f;
+    const int64_t n_out = (int64_t)out_h * out_w * C;
+    float* resized = (is_psf && (flags & LPC_IO_SINGLE_PSF) && C > 1) ? sc.get<float>((size_t)n_out) : dev_out;
+    if (!resized) return LPC_ENOMEM;
+    int rc = io_resize(sc, src, resized, 1, H, W, C, out_h, out_w, st);
+    if (rc) return rc;
+    float* fin = resized;
+    if (is_psf && (flags & LPC_IO_SINGLE_PSF) && C > 1) {  // io.py:363-368
+        k_io_sum_channels<<<nb, 256, 0, st>>>(resized, dev_out, (int64_t)out_h * out_w, C);
+        fin = dev_out; Cc = 1;
+    }
+    const int64_t nf = (int64_t)out_h * out_w * Cc;
+    if (is_psf || (normalize && !norm_first)) {
+        k_io_reduce<<<(unsigned)std::min<int64_t>((nf + 255) / 256, 148 * 8), 256, 0, st>>>(fin, nf, sumsq, vmax);
+        k_io_normalize<<<(unsigned)std::min<int64_t>((nf + 255) / 256, 148 * 32), 256, 0, st>>>(fin, nf, sumsq, vmax, is_psf ? 0 : 1);
+    }
+    if (is_psf && bg1 > bg0) k_io_scale_vec<<<1, 32, 0, st>>>(dev_bg_out, C, maxval);  // io.py:376: bg /= max_val
+    return cudaGetLastError() == cudaSuccess ? LPC_OK : LPC_ECUDA;
+}
+}  // namespace
+
 // ====================================================================================
 // C-ABI
 // ====================================================================================
@@ -1838,6 +1967,37 @@ int lpc_op_finite_diff_gram(int device, int dtype, void* dev_out, int D, int Hp,
     if (dtype == LPC_F32) k_op_finite_diff_gram<float><<<op_blocks(n), 256, 0, st>>>((float2*)dev_out, D, Hp, Wp, Nh, C);
     else k_op_finite_diff_gram<double><<<op_blocks(n), 256, 0, st>>>((double2*)dev_out, D, Hp, Wp, Nh, C);
     LPC_OP_EPILOGUE();
+}
+
+
+int lpc_io_load_psf(int device, int raw_bits, const void* dev_raw, int H, int W, int C, int flags, int bg_pix0, int bg_pix1,
+                    int out_h, int out_w, void* dev_psf_out, void* dev_bg_out, void* stream) {
+    if (!dev_raw || !dev_psf_out || H < 1 || W < 1 || (C != 1 && C != 3) || out_h < 1 || out_w < 1) return LPC_EINVAL;
+    if (raw_bits != 8 && raw_bits != 16) return LPC_EINVAL;
+    DeviceGuard guard(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (raw_bits == 8) return io_load<uint8_t>(1, (const uint8_t*)dev_raw, H, W, C, flags, bg_pix0, bg_pix1, nullptr, out_h, out_w, 1,
+                                               (float*)dev_psf_out, (float*)dev_bg_out, st);
+    return io_load<uint16_t>(1, (const uint16_t*)dev_raw, H, W, C, flags, bg_pix0, bg_pix1, nullptr, out_h, out_w, 1,
+                             (float*)dev_psf_out, (float*)dev_bg_out, st);
+}
+int lpc_io_load_image(int device, int raw_bits, const void* dev_raw, int H, int W, int C, int flags, const void* dev_bg,
+                      int out_h, int out_w, int normalize, void* dev_out, void* stream) {
+    if (!dev_raw || !dev_out || H < 1 || W < 1 || (C != 1 && C != 3) || out_h < 1 || out_w < 1) return LPC_EINVAL;
+    if (raw_bits != 8 && raw_bits != 16) return LPC_EINVAL;
+    DeviceGuard guard(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (raw_bits == 8) return io_load<uint8_t>(0, (const uint8_t*)dev_raw, H, W, C, flags, 0, 0, (const float*)dev_bg, out_h, out_w, normalize,
+                                               (float*)dev_out, nullptr, st);
+    return io_load<uint16_t>(0, (const uint16_t*)dev_raw, H, W, C, flags, 0, 0, (const float*)dev_bg, out_h, out_w, normalize,
+                             (float*)dev_out, nullptr, st);
+}
+int lpc_io_rgb2gray(int device, const void* dev_rgb, void* dev_gray, int64_t npix, void* stream) {
+    if (!dev_rgb || !dev_gray || npix < 0) return LPC_EINVAL;
+    DeviceGuard guard(device);
+    if (npix == 0) return LPC_OK;
+    k_io_rgb2gray<<<op_blocks(npix), 256, 0, (cudaStream_t)stream>>>((const float*)dev_rgb, (float*)dev_gray, npix);
+    return cudaGetLastError() == cudaSuccess ? LPC_OK : LPC_ECUDA;
 }
 
 int lpc_bytes_per_iter(lpc_plan_t plan, double* algorithmic_bytes) {

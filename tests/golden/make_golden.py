@@ -231,6 +231,69 @@ def make_pnp(lensless, torch):
     print("wrote pnp.npz", {k: float(np.abs(v).max()) for k, v in store.items() if "_t32_" in k})
 
 
+def make_loader(lensless, torch):
+    """``loader.npz`` + small raw frames (``raw_psf.png``, ``raw_data.png``: synthetic 12-bit BGR uint16; ``raw8_*.png``:
+    8-bit; ``real_*_crop.png``: a 456x608 crop of the reference's bundled tape PSF / thumbs-up measurement): outputs of the
+    reference's own ``load_data`` / ``load_psf`` / ``load_image`` (io.py:20-600) on them, for the GPU loader's parity."""
+    import cv2
+    from lensless.utils.io import load_data, load_image, load_psf
+
+    rng = np.random.default_rng(123)
+    H, W = 304, 404
+    yy, xx = np.mgrid[0:H, 0:W]
+    psf = np.full((H, W, 3), 64.0) + rng.normal(0, 3, (H, W, 3))
+    for _ in range(60):  # caustic-like bright spots
+        cy, cx, a = rng.integers(30, H - 30), rng.integers(30, W - 30), rng.uniform(300, 3500)
+        spot = a * np.exp(-(((yy - cy) / rng.uniform(1.5, 4)) ** 2 + ((xx - cx) / rng.uniform(1.5, 4)) ** 2))
+        psf += spot[:, :, None] * rng.uniform(0.6, 1.0, 3)
+    data = np.full((H, W, 3), 64.0) + rng.normal(0, 3, (H, W, 3))
+    for _ in range(8):
+        cy, cx, a = rng.integers(40, H - 40), rng.integers(40, W - 40), rng.uniform(500, 2500)
+        blob = a * np.exp(-(((yy - cy) / rng.uniform(20, 60)) ** 2 + ((xx - cx) / rng.uniform(20, 60)) ** 2))
+        data += blob[:, :, None] * rng.uniform(0.5, 1.0, 3)
+    files = {}
+    for name, arr in (("raw_psf", psf), ("raw_data", data)):
+        fp = os.path.join(HERE, name + ".png")
+        cv2.imwrite(fp, np.clip(arr, 0, 4095).astype(np.uint16))
+        files[name] = fp
+        fp8 = os.path.join(HERE, name.replace("raw_", "raw8_") + ".png")
+        cv2.imwrite(fp8, np.clip(arr / 16, 0, 255).astype(np.uint8))
+        files[name.replace("raw_", "raw8_")] = fp8
+    for name, src in (("real_psf_crop", "data/psf/tape_rgb.png"), ("real_data_crop", "data/raw_data/thumbs_up_rgb.png")):
+        img = cv2.imread(os.path.join(REF, src), cv2.IMREAD_UNCHANGED)
+        fp = os.path.join(HERE, name + ".png")
+        cv2.imwrite(fp, np.ascontiguousarray(img[1292:1748, 1724:2332]))
+        files[name] = fp
+    store = {}
+    cases = {
+        "ds4": dict(downsample=4, normalize=True),
+        "ds4_nonorm": dict(downsample=4),
+        "ds2_gray": dict(downsample=2, gray=True, normalize=True),
+        "ds4_flip": dict(downsample=4, flip=True, normalize=True),
+        "ds4_fliplr": dict(downsample=4, flip_lr=True, normalize=True),
+        "ds3_single": dict(downsample=3, single_psf=True, normalize=True),
+        "ds4_nobg": dict(downsample=4, bg_pix=None, normalize=True),
+        "shape": dict(shape=(1, 100, 150, 3), downsample=2, normalize=True),  # (the reference needs a downsample next to shape: io.py:360)
+        "ds1p6": dict(downsample=1.6, normalize=True),
+    }
+    for tag, kw in cases.items():
+        if tag == "ds3_single":  # the reference then repeats the 1-channel PSF across the RGB data's channels
+            psf_o, data_o = load_data(files["raw_psf"], files["raw_data"], plot=False, dtype="float32", **kw)
+        else:
+            psf_o, data_o = load_data(files["raw_psf"], files["raw_data"], plot=False, dtype="float32", **kw)
+        store[f"{tag}_psf"], store[f"{tag}_data"] = np.asarray(psf_o, np.float32), np.asarray(data_o, np.float32)
+    psf_o, data_o, bg_o = load_data(files["raw8_psf"], files["raw8_data"], plot=False, dtype="float32", downsample=4, normalize=True, return_bg=True)
+    store["u8_ds4_psf"], store["u8_ds4_data"], store["u8_ds4_bg"] = np.asarray(psf_o, np.float32), np.asarray(data_o, np.float32), np.asarray(bg_o, np.float32)
+    psf_o, data_o, bg_o = load_data(files["real_psf_crop"], files["real_data_crop"], plot=False, dtype="float32", downsample=4, normalize=True, return_bg=True)
+    store["real_ds4_psf"], store["real_ds4_data"], store["real_ds4_bg"] = np.asarray(psf_o, np.float32), np.asarray(data_o, np.float32), np.asarray(bg_o, np.float32)
+    p, b = load_psf(files["raw_psf"], downsample=4, return_bg=True)
+    store["load_psf_ds4"], store["load_psf_ds4_bg"] = p, b
+    store["load_image_ds4"] = load_image(files["raw_data"], downsample=4, return_float=True, as_4d=True, bg=b)
+    store["load_image_full_nonorm"] = load_image(files["raw_data"], return_float=True, normalize=False)
+    np.savez_compressed(os.path.join(HERE, "loader.npz"), **store)
+    print("wrote loader.npz", {k: v.shape for k, v in store.items()})
+
+
 def make_recon_error(lensless, torch):
     """``recon_error.npz``: reconstruction_error (recon.py:607-653) of ADMM (pad=False branch) and FISTA (pad=True
     branch) on a small case, normalised and raw, default arguments and explicit (prediction, lensless, psfs)."""
@@ -278,6 +341,8 @@ def main():
         return make_recon_error(lensless, torch)
     if "--only-pnp" in sys.argv:
         return make_pnp(lensless, torch)
+    if "--only-loader" in sys.argv:
+        return make_loader(lensless, torch)
 
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -398,6 +463,8 @@ def main():
     make_bundled_large(lensless, torch)
     make_recon_error(lensless, torch)
     make_pnp(lensless, torch)
+    make_loader(lensless, torch)
+    make_loader(lensless, torch)
 
 
 if __name__ == "__main__":

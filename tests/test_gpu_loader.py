@@ -1,0 +1,81 @@
+"""
+GPU loader (lenslesspicam_b200.io, csrc/lpc_io.cuh) against the reference's own ``load_data`` / ``load_psf`` /
+``load_image`` outputs on the raw frames committed next to the goldens (tests/golden/make_golden.py::make_loader):
+synthetic 12-bit and 8-bit frames and a crop of the reference's bundled tape PSF / thumbs-up measurement.
+Tolerance: float32 round-off of the resize accumulation (1e-6 relative to the maximum); integer geometry exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, rel_to_max
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+def fp(name):
+    return os.path.join(GOLDEN, name + ".png")
+
+
+CASES = {
+    "ds4": dict(downsample=4, normalize=True),
+    "ds4_nonorm": dict(downsample=4),
+    "ds2_gray": dict(downsample=2, gray=True, normalize=True),
+    "ds4_flip": dict(downsample=4, flip=True, normalize=True),
+    "ds4_fliplr": dict(downsample=4, flip_lr=True, normalize=True),
+    "ds3_single": dict(downsample=3, single_psf=True, normalize=True),
+    "ds4_nobg": dict(downsample=4, bg_pix=None, normalize=True),
+    "shape": dict(shape=(1, 100, 150, 3), downsample=2, normalize=True),
+    "ds1p6": dict(downsample=1.6, normalize=True),
+}
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_load_data_matches_reference(tag):
+    import lenslesspicam_b200 as L
+
+    g = load_golden("loader")
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        psf, data = L.load_data(fp("raw_psf"), fp("raw_data"), **CASES[tag])
+    assert psf.is_cuda and psf.dtype == torch.float32 and tuple(psf.shape) == g[f"{tag}_psf"].shape
+    assert tuple(data.shape) == g[f"{tag}_data"].shape
+    assert rel_to_max(psf.cpu().numpy(), g[f"{tag}_psf"]) <= TOL, rel_to_max(psf.cpu().numpy(), g[f"{tag}_psf"])
+    assert rel_to_max(data.cpu().numpy(), g[f"{tag}_data"]) <= TOL, rel_to_max(data.cpu().numpy(), g[f"{tag}_data"])
+
+
+def test_8bit_and_real_frames_and_single_functions():
+    import lenslesspicam_b200 as L
+
+    g = load_golden("loader")
+    for tag, p, d in (("u8_ds4", "raw8_psf", "raw8_data"), ("real_ds4", "real_psf_crop", "real_data_crop")):
+        psf, data, bg = L.load_data(fp(p), fp(d), downsample=4, normalize=True, return_bg=True)
+        assert rel_to_max(psf.cpu().numpy(), g[f"{tag}_psf"]) <= TOL
+        assert rel_to_max(data.cpu().numpy(), g[f"{tag}_data"]) <= TOL
+        assert rel_to_max(bg.cpu().numpy(), g[f"{tag}_bg"]) <= TOL
+    psf, bg = L.load_psf(fp("raw_psf"), downsample=4, return_bg=True)
+    assert rel_to_max(psf.cpu().numpy(), g["load_psf_ds4"]) <= TOL and rel_to_max(bg.cpu().numpy(), g["load_psf_ds4_bg"]) <= TOL
+    assert abs(float(psf.double().pow(2).sum().sqrt()) - 1.0) <= 1e-6  # L2-normalised (io.py:375)
+    img = L.load_image(fp("raw_data"), downsample=4, return_float=True, as_4d=True, bg=bg)
+    assert rel_to_max(img.cpu().numpy(), g["load_image_ds4"]) <= TOL
+    full = L.load_image(fp("raw_data"), return_float=True, normalize=False)
+    assert np.array_equal(full.cpu().numpy(), g["load_image_full_nonorm"])  # BGR->RGB + cast only: exact
+
+
+def test_loaded_data_reconstructs_like_the_reference_inputs():
+    """end to end: raw frames -> GPU loader -> ADMM on the engine == the reference's loader -> the CPU oracle"""
+    import lensless_oracle as orc
+    import lenslesspicam_b200 as L
+
+    g = load_golden("loader")
+    psf, data = L.load_data(fp("real_psf_crop"), fp("real_data_crop"), downsample=4, normalize=True)
+    rec = L.ADMM(psf)
+    rec.set_data(data)
+    out = rec.apply(n_iter=10, disp_iter=None, plot=False).cpu().numpy()
+    ref = orc.reconstruct("admm", g["real_ds4_psf"], g["real_ds4_data"], 10)
+    assert rel_to_max(out, ref) <= 1e-5
