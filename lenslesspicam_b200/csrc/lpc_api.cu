@@ -1645,29 +1645,28 @@ namespace {
 // weights of one antialiased axis (ATen UpSampleKernel.cpp: _compute_indices_min_size_weights_aa with the triangle
 // filter, float arithmetic as for float32 images); returns max_w
 int aa_axis_weights(int n_in, int n_out, std::vector<int2>* idx, std::vector<float>* wts) {
+    // expression types as in ATen (scalar_t = float for float32 images; the 0.5 / 1.0 literals are doubles there too)
     const float scale = (float)n_in / (float)n_out;  // area_pixel_compute_scale, align_corners = false, no scale factor
-    const float support = (scale >= 1.0f) ? 1.0f * scale : 1.0f;  // interp_size 2 -> * 0.5 * 2
+    const float support = (scale >= 1.0) ? (float)((2 * 0.5) * scale) : (float)(2 * 0.5);
     const int max_w = (int)std::ceil(support) * 2 + 1;
     idx->assign(n_out, int2{0, 0});
     wts->assign((size_t)n_out * max_w, 0.0f);
-    const float invscale = (scale >= 1.0f) ? 1.0f / scale : 1.0f;
+    const float invscale = (scale >= 1.0) ? (float)(1.0 / scale) : 1.0f;
     for (int i = 0; i < n_out; ++i) {
-        const float center = scale * (i + 0.5f);
-        int64_t xmin = (int64_t)(center - support + 0.5f);
-        if (xmin < 0) xmin = 0;
-        int64_t xmax = (int64_t)(center + support + 0.5f);
-        if (xmax > n_in) xmax = n_in;
-        const int xsize = (int)(xmax - xmin);
+        const float center = (float)(scale * (i + 0.5));
+        int64_t xmin = std::max((int64_t)(center - support + 0.5), (int64_t)0);
+        int64_t xsize = std::min((int64_t)(center + support + 0.5), (int64_t)n_in) - xmin;
+        xsize = std::min(std::max(xsize, (int64_t)0), (int64_t)max_w);
         float total = 0.0f;
         float* w = wts->data() + (size_t)i * max_w;
-        for (int j = 0; j < xsize; ++j) {
-            float x = ((float)(j + xmin) - center + 0.5f) * invscale;
+        for (int64_t j = 0; j < xsize; ++j) {
+            float x = (float)((j + xmin - center + 0.5) * invscale);
             x = std::fabs(x);
             w[j] = x < 1.0f ? 1.0f - x : 0.0f;
             total += w[j];
         }
-        if (total != 0.0f) for (int j = 0; j < xsize; ++j) w[j] /= total;
-        (*idx)[i] = int2{(int)xmin, xsize};
+        if (total != 0.0f) for (int64_t j = 0; j < xsize; ++j) w[j] /= total;
+        (*idx)[i] = int2{(int)xmin, (int)xsize};
     }
     return max_w;
 }
