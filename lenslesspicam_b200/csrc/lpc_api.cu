@@ -1091,8 +1091,8 @@ struct Plan : lpc_plan_s {
             if (mom) LPC_CK(cudaMemsetAsync(mom, 0, (size_t)Np * h * w * sizeof(T), st));
             if (n_sched > 0 && algo == LPC_ALGO_FISTA) {
                 // unrolled_fista.py:95-100: the previous iterate starts as the initial estimate itself
-                if (!gd2) return fail(LPC_ENOTIMPL, "reset", "unrolled FISTA schedules need the fused engine (fp32, menu sizes)");
-                LPC_CK(cudaMemcpyAsync(mom, xu, (size_t)Np * h * w * sizeof(T), cudaMemcpyDeviceToDevice, st));
+                if (gd2) LPC_CK(cudaMemcpyAsync(mom, xu, (size_t)Np * h * w * sizeof(T), cudaMemcpyDeviceToDevice, st));
+                else if ((rc = copy_window(xpad, mom, st))) return rc;
             }
             gd_it = 0;
             tk = tk0;            // gd.py:227-233
