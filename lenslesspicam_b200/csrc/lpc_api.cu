@@ -19,6 +19,7 @@
 #include "lpc_fused.cuh"
 #include "lpc_fused_gd.cuh"
 #include "lpc_fused_tma.cuh"
+#include "lpc_fused_rows_tma.cuh"
 #include "lpc_gd.cuh"
 #include "lpc_metrics.cuh"
 #include "lpc_io.cuh"
@@ -75,6 +76,7 @@ template <> struct FftTraits<double> {
 // ---- compiled menu of the fused engine (float only): padded size -> kernel instantiation
 namespace {
 using IfftKern = void (*)(FusedK, const float2*, const float2*, float*);
+using IfftTmaKern = void (*)(FusedK, const CUtensorMap, int, const float2*, float*);
 using FftKern = void (*)(FusedK, const float2*, const float*, float2*, float);
 using SpatKern = void (*)(FusedK, AdmmK<float>, const float2*, const float*, float2*, const float*, float*, float*,
                           const float*, float*);
@@ -83,7 +85,8 @@ using ColsKern = void (*)(FusedK, const float2*, const float2*, const float2*, f
 using GdRowsKern = void (*)(GdFusedK, const float2*, const float2*, float2*, const float*, float*, float*, const float*,
                             float, int);
 using GdColsKern = void (*)(GdFusedK, const float2*, const float2*, float2*, const float2*);
-struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; GdRowsKern gd[5]; };
+struct RowsEntry { int N, npass, radix[4]; IfftKern ifft; FftKern fft; SpatKern spatial[3]; GdRowsKern gd[5]; IfftTmaKern ifft_tma;
+                   size_t smem_ifft_tma; int nbox, boxt; };
 using ColsTmaKern = void (*)(FusedK, ColsTmaK, int, const float2*, const float2*, float2*, const float2*, const float*,
                              const float2*);
 // threads per compute group of the persistent column kernel: two groups of 288 (measured at Hp = 2160, A per launch:
@@ -99,7 +102,9 @@ template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
       k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 4>},                                                       \
      {k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 0>, k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 1>,                   \
       k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 2>, k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 3>,                   \
-      k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 4>}},
+      k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 4>},                                                                \
+     k_rows_ifft_tma<float, FftSeq<N, __VA_ARGS__>>, rows_ifft_tma_smem_bytes<FftSeq<N, __VA_ARGS__>>(),            \
+     RowBoxes<(N / 2 + 1 + LPC_NCT - 1) / LPC_NCT>::NBOX, RowBoxes<(N / 2 + 1 + LPC_NCT - 1) / LPC_NCT>::BOXT},
 const RowsEntry g_rows_menu[] = {LPC_ROW_MENU(LPC_X)};
 #undef LPC_X
 #define LPC_X(N, ...) \
@@ -486,9 +491,51 @@ struct Plan : lpc_plan_s {
         fk.pack_s = std::ldexp(1.0f, es); fk.inv_pack_s = std::ldexp(1.0f, -es);
     }
     int next_dir() { const int d = dir_enable ? dir_toggle : 0; dir_toggle ^= 1; return d; }
+    // B1 through the TMA unit (lpc_fused_rows_tma.cuh): a tensor map over Tin, persistent CTAs
+    int b1_tma = 0;
+    CUtensorMap tin_map{};
+    int init_b1_tma(int max_optin) {
+        if constexpr (!std::is_same<T, float>::value) {
+            return LPC_OK;
+        } else {
+            int want = 1;
+            if (const char* e = getenv("LPC_B1_TMA")) want = atoi(e) ? 1 : 0;
+            if (!want || rows_entry->smem_ifft_tma > (size_t)max_optin) return LPC_OK;
+            using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+                qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return LPC_OK; }
+            const cuuint64_t gdim[3] = {8, (cuuint64_t)Hp, (cuuint64_t)Np * fk.NT};
+            const cuuint64_t gstr[2] = {32, (cuuint64_t)Hp * 32};
+            const cuuint32_t box[3] = {8, 1, (cuuint32_t)rows_entry->boxt};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = ((EncodeFn)fn)(&tin_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)Tin, gdim, gstr, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return LPC_OK;  // the LDG gather serves
+            LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->ifft_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)rows_entry->smem_ifft_tma));
+            LPC_CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+            b1_tma = 1;
+            return LPC_OK;
+        }
+    }
     int launch_rows_ifft(cudaStream_t st, int p0 = 0, int np = -1, T* vh = nullptr) {
         if constexpr (std::is_same<T, float>::value) {
             if (np < 0) np = Np;
+            if (b1_tma) {
+                FusedK k = fk; k.plane0 = p0; k.rev = next_dir();
+                const int n_items = Hp * np;
+                int per_sm = 3;
+                if (const char* e = getenv("LPC_B1_CTAS")) per_sm = atoi(e);
+                const int nblk = n_items < n_sms * per_sm ? n_items : n_sms * per_sm;
+                rows_entry->ifft_tma<<<nblk, LPC_ROWS_THREADS, rows_entry->smem_ifft_tma, st>>>(k, tin_map, n_items, tw_row, vh ? vh : VH);
+                LPC_KCHECK();
+                return LPC_OK;
+            }
             dim3 grid(Hp, np);
             FusedK k = fk; k.plane0 = p0; k.rev = next_dir();
             rows_entry->ifft<<<grid, LPC_ROWS_THREADS, smem_row, st>>>(k, tw_row, Tin, vh ? vh : VH);
@@ -585,6 +632,7 @@ struct Plan : lpc_plan_s {
             if ((rc = alloc(&Rt, (size_t)PQ * fk.NT * Hp * LPC_NCT))) return rc;
             if ((rc = upload_twiddles())) return rc;
             if ((rc = init_cols_tma(max_optin))) return rc;
+            if ((rc = init_b1_tma(max_optin))) return rc;
             v2 = true;
             return LPC_OK;
         }
