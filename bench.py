@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=1, help="PSF depth D > 1: BASELINE configs[4], D independent 2-D problems "
                     "against one measurement (ADMM(allow_depth=True); the reference has no 3-D ADMM, SURVEY 8a note)")
     ap.add_argument("--configs", default="default", help="'default' = every BASELINE config next to the headline when the "
-                    "headline shape is benchmarked, 'none', or a comma list of fista300,bundled,depth16,batch256")
+                    "headline shape is benchmarked, 'none', or a comma list of fista300,bundled,depth16,raw,batch256")
     ap.add_argument("--batch256-n", type=int, default=256, help="measurements of the sharded-batch config (BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip cpu_baseline / torch_baseline_gpu / parity")
     ap.add_argument("--no-graph", action="store_true")
@@ -428,7 +428,7 @@ def main():
     D = args.depth
     headline = (args.algo == "admm" and D == 1 and n_iter == 100 and (h, w, C, Bg) == (1080, 1920, 3, 1) and args.engine is None)
     if args.configs == "default":
-        want = {"fista300", "bundled", "depth16", "batch256"} if headline else set()
+        want = {"fista300", "bundled", "depth16", "raw", "batch256"} if headline else set()
     elif args.configs == "none":
         want = set()
     else:
@@ -569,6 +569,50 @@ def main():
             cfgs["depth16_admm50"] = bench_config("admm", dp, dm, 50, 3, allow_depth=True)
             cfgs["depth16_admm50"]["workload"] = workload("admm", 50, 1, h, w, D=16)
             del dp, dm
+        if "raw" in want:
+            # from a raw 12-bit sensor frame in pinned host memory to the image, per step: H2D of the
+            # uint16 frame (3040x4056x3, the bundled data's size), GPU loader (BGR->RGB, background subtraction, clip,
+            # antialiased downsample x4 -> 760x1014, max-normalise), ADMM-100 on the fused engine, D2H of the image
+            from lenslesspicam_b200 import io as lio
+
+            Hr, Wr = 3040, 4056
+            gen = torch.Generator().manual_seed(5)
+            raw_psf = (torch.rand((Hr, Wr, 3), generator=gen) ** 12 * 3900 + 64).to(torch.int16)
+            raw_meas = (torch.rand((Hr, Wr, 3), generator=gen) * 2000 + 64).to(torch.int16).pin_memory()
+            hh, ww = Hr // 4, Wr // 4
+            rpsf = torch.empty((1, hh, ww, 3), dtype=torch.float32, device=device)
+            rbg = torch.zeros((3,), dtype=torch.float32, device=device)
+            d_raw = raw_psf.to(device)
+            _lib.check(lib.lpc_io_load_psf(local, 16, d_raw.data_ptr(), Hr, Wr, 3, lio.IO_BGR, 5, 25, hh, ww, rpsf.data_ptr(), rbg.data_ptr(), stream.cuda_stream))
+            rrec = L.ADMM(rpsf, n_iter=100)
+            rdata = torch.empty((1, 1, hh, ww, 3), dtype=torch.float32, device=device)
+            rout = torch.empty((1, hh, ww, 3), dtype=torch.float32).pin_memory()
+            d_meas = torch.empty((Hr, Wr, 3), dtype=torch.int16, device=device)
+
+            def step_raw():
+                d_meas.copy_(raw_meas, non_blocking=True)
+                _lib.check(lib.lpc_io_load_image(local, 16, d_meas.data_ptr(), Hr, Wr, 3, lio.IO_BGR | lio.IO_NORMALIZE_FIRST, rbg.data_ptr(),
+                                                 hh, ww, 1, rdata.data_ptr(), stream.cuda_stream))
+                rrec.set_data(rdata)
+                rout.copy_(rrec.apply(disp_iter=None, plot=False), non_blocking=True)
+                stream.synchronize()
+
+            for _ in range(3):
+                step_raw()
+            ms_raw = timed(step_raw, 5) / 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                _lib.check(lib.lpc_io_load_image(local, 16, d_meas.data_ptr(), Hr, Wr, 3, lio.IO_BGR | lio.IO_NORMALIZE_FIRST, rbg.data_ptr(),
+                                                 hh, ww, 1, rdata.data_ptr(), stream.cuda_stream))
+            e1.record(stream)
+            stream.synchronize()
+            cfgs["raw_frame_to_image"] = {
+                "value": world * 1e3 / ms_raw, "unit": UNIT, "ms_per_step": ms_raw, "loader_ms": e0.elapsed_time(e1) / 5,
+                "h2d_bytes_per_step": int(Hr * Wr * 3 * 2), "d2h_bytes_per_step": int(hh * ww * 3 * 4), "engine_version": rrec.engine_version,
+                "workload": f"raw uint16 {Hr}x{Wr}x3 frame (pinned host) -> GPU loader (load_data arithmetic, downsample 4) -> ADMM-100 @ 3x{hh}x{ww} -> image in host memory",
+            }
+            del rrec, d_raw, d_meas, rdata, rpsf
         del recon
         torch.cuda.empty_cache()
         if "batch256" in want:

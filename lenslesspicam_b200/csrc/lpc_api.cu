@@ -98,8 +98,7 @@ template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }
 #define LPC_X(N, ...)                                                                                   \
     {N, seq_len<__VA_ARGS__>(), {__VA_ARGS__}, k_rows_ifft<float, FftSeq<N, __VA_ARGS__>>,              \
      k_rows_fft<float, FftSeq<N, __VA_ARGS__>>,                                                         \
-     {k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 1>, k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 2>, \
-      k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 4>},                                                       \
+     {k_rows_spatial_fft<float, FftSeq<N, __VA_ARGS__>, 1>, nullptr, nullptr},                                       \
      {k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 0>, k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 1>,                   \
       k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 2>, k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 3>,                   \
       k_gd_rows<float, FftSeq<N, __VA_ARGS__>, 4>},                                                                \
@@ -610,11 +609,11 @@ struct Plan : lpc_plan_s {
             if (smem_row > (size_t)max_optin || smem_col > (size_t)max_optin) return LPC_OK;
             LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
             LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
-            for (int v = 0; v < 3; ++v)
-                LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->spatial[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
+            LPC_CK(cudaFuncSetAttribute((const void*)rows_entry->spatial[0], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_row));
             for (int v = 0; v < 2; ++v)
                 LPC_CK(cudaFuncSetAttribute((const void*)cols_entry->kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_col));
-            if (const char* e = getenv("LPC_RY")) { int r = atoi(e); ry_log2 = r >= 4 ? 2 : r >= 2 ? 1 : 0; }
+            // non-TMA column kernel: 576 threads x 2 CTAs/SM when two tiles fit an SM, else 1024 threads x 1 (large Hp)
+            cols_variant = (2 * (smem_col + 1024) <= (size_t)228 * 1024) ? 1 : 0;
             if (const char* e = getenv("LPC_COLS_VARIANT")) cols_variant = atoi(e) ? 1 : 0;
 
             fk.Hp = Hp; fk.Wp = Wp; fk.Nh = Nh; fk.NT = (Nh + LPC_NCT - 1) / LPC_NCT;

@@ -622,3 +622,30 @@ def test_plug_and_play_matches_reference():
     assert rel_to_max(out, g["fista_boxproj_t32_8"]) <= TOL
     with pytest.raises(NotImplementedError):
         L().ADMM(dev(g["psf"]), denoiser={"network": "NoSuchNet", "noise_level": 1})
+
+
+# ------------------------------------------------------------------------------ the widened size menu
+MENU_SHAPES = [(64, 100), (100, 64), (120, 128), (128, 120), (160, 180), (180, 160), (200, 300), (300, 200), (320, 360),
+               (360, 320), (400, 600), (600, 400), (640, 720), (720, 640), (800, 1200), (1200, 800), (1280, 1440),
+               (1440, 1280), (1536, 1600), (1600, 1536), (2048, 1920), (1920, 2048)]
+
+
+@pytest.mark.parametrize("shape", MENU_SHAPES)
+def test_every_menu_size_runs_the_fused_engine_and_agrees_with_the_cufft_engine(shape):
+    """Padded sizes next_fast_len(2d-1) of the usual sensor dimensions are compiled into the fused engine (rows and
+    columns independently, csrc/lpc_fused.cuh); each row / column instantiation is exercised once here against the
+    cuFFT engine (same algebra, library transforms) and, for the small ones, against the CPU oracle."""
+    h, w = shape
+    rng = np.random.default_rng(h * 7919 + w)
+    psf = (rng.random((1, h, w, 1)) ** 8).astype(np.float32)
+    psf /= np.linalg.norm(psf.ravel())
+    data = rng.random((1, h, w, 1)).astype(np.float32)
+    for algo, n in (("admm", 4), ("fista", 4)):
+        a, ra = run(algo, psf, data, n)
+        b, rb = run(algo, psf, data, n, engine="v1")
+        assert _engine_version(ra) == 2 and _engine_version(rb) == 1, (shape, algo)
+        assert rel_to_max(a.cpu().numpy(), b.cpu().numpy()) <= 3e-6, (shape, algo, rel_to_max(a.cpu().numpy(), b.cpu().numpy()))
+        if h * w <= 400 * 600:
+            assert rel_to_max(a.cpu().numpy(), orc.reconstruct(algo, psf, data, n)) <= TOL, (shape, algo)
+        del ra, rb
+    torch.cuda.empty_cache()
