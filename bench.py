@@ -619,18 +619,18 @@ def main():
             # BASELINE configs[3]: N host-resident measurements, batch axis sharded over the ranks, every measurement
             # copied H2D and its image D2H inside the timed region; time-to-solution = max over ranks
             NB = args.batch256_n
-            gen = torch.Generator().manual_seed(77)
             base = meas[0:1].cpu()
-            host_batch = torch.empty((NB, 1, h, w, C), dtype=torch.float32).pin_memory()
-            for i in range(NB):  # distinct measurements (a cheap roll of a synthetic one); identical on every rank
-                host_batch[i] = torch.roll(base[0], shifts=(7 * i) % h, dims=1)
+            mine_idx = lpd.shard_batch(NB, world, rank)
+            n_mine = len(mine_idx)
+            host_batch = torch.empty((n_mine, 1, h, w, C), dtype=torch.float32).pin_memory()  # this rank's shard only
+            for k, i in enumerate(mine_idx):  # distinct measurements (a cheap roll of a synthetic one)
+                host_batch[k] = torch.roll(base[0], shifts=(7 * i) % h, dims=1)
             solver = L.ADMM(psf, n_iter=100)
-            lpd.reconstruct_sharded(host_batch[: 2 * world], psf, n_iter=100, solver=solver)  # warm-up: plans, graphs
-            n_mine = len(lpd.shard_batch(NB, world, rank))
+            lpd.reconstruct_sharded(host_batch[:2], psf, n_iter=100, solver=solver, total=2 * world)  # warm-up: plans, graphs
             out_buf = torch.empty((n_mine, 1, h, w, C), dtype=torch.float32).pin_memory()  # the caller's result buffer
             barrier()
             t0 = time.perf_counter()
-            local_out, mine = lpd.reconstruct_sharded(host_batch, psf, n_iter=100, solver=solver, out=out_buf)
+            local_out, mine = lpd.reconstruct_sharded(host_batch, psf, n_iter=100, solver=solver, out=out_buf, total=NB)
             torch.cuda.synchronize(device)
             dt_ms = lpd.max_over_ranks((time.perf_counter() - t0) * 1e3, device=device)
             bpi = 100 * solver.bytes_per_iter()  # per image (plans of batch 1)

@@ -670,6 +670,8 @@ struct Plan : lpc_plan_s {
                 const Cplx sy = phase((long long)m * NBL * h2, Hp);
                 ctk.sym[m].x = sy.x; ctk.sym[m].y = sy.y;
             }
+            ctk.s_folded = (Hp % 2 == 0 && Wp % 2 == 0) ? 1 : 0;
+            if (const char* e = getenv("LPC_S_FOLDED")) ctk.s_folded = (atoi(e) && ctk.s_folded) ? 1 : 0;
             int rc;
             if ((rc = alloc(&tabs_ip, tabs.size()))) return rc;
             LPC_CK(cudaMemcpy(tabs_ip, tabs.data(), tabs.size() * sizeof(Cplx), cudaMemcpyHostToDevice));
@@ -822,7 +824,9 @@ struct Plan : lpc_plan_s {
         LPC_KCHECK();
         if constexpr (std::is_same<T, float>::value) {
             if (cols_tma) {
-                k_tile_H_mid<T><<<1184, 256, 0, st>>>(Hc, kymap, Hm, PQ, Hp, Nh, fk.NT, cols_entry->radix[cols_entry->npass - 1]);
+                const bool fold = ctk.s_folded != 0;
+                k_tile_H_mid<T><<<1184, 256, 0, st>>>(Hc, kymap, Hm, PQ, Hp, Nh, fk.NT, cols_entry->radix[cols_entry->npass - 1],
+                                                     fold ? Sy : nullptr, fold ? Sx : nullptr);
                 LPC_KCHECK();
             }
         }

@@ -319,8 +319,12 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                         Vec16<T> lo, hi;
                         lo.v[0] = av[0]; lo.v[1] = xin.v[0] * f.pack_s; lo.v[2] = av[1]; lo.v[3] = xin.v[1] * f.pack_s;
                         hi.v[0] = av[2]; hi.v[1] = xin.v[2] * f.pack_s; hi.v[2] = av[3]; hi.v[3] = xin.v[3] * f.pack_s;
-                        *reinterpret_cast<Vec16<T>*>(W + j) = lo;
-                        *reinterpret_cast<Vec16<T>*>(W + j + 2) = hi;
+                        // a lane's two 16-byte pieces are 32 bytes apart from its neighbour's: written in the same order by
+                        // all lanes, lanes q and q+4 of a quarter-warp hit the same banks (2-way conflict, measured 2x the ideal
+                        // wavefronts).  Lanes 4..7 of every 8 store their pieces in the opposite order.
+                        const bool sw = (q >> 2) & 1;
+                        *reinterpret_cast<Vec16<T>*>(W + j + (sw ? 2 : 0)) = sw ? hi : lo;
+                        *reinterpret_cast<Vec16<T>*>(W + j + (sw ? 0 : 2)) = sw ? lo : hi;
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) { C z; z.x = av[e]; z.y = xin.v[e] * f.pack_s; W[fft_pad(j + e, PADSH)] = z; }

@@ -95,6 +95,8 @@ struct ColsTmaK {
     float cm[LPC_TMA_MAXR];     // cos(2 pi m / RL)
     float sm[LPC_TMA_MAXR];     // sin(2 pi m / RL)
     float2 sym[LPC_TMA_MAXR];   // Sy[m * Hp/RL]: ifftshift phase of the innermost digit
+    int s_folded;               // 1: Hm holds S*H (both padded sizes even: the ifftshift phase S is +-1, real), so
+                                // S*conj(H) = conj(S*H) and the stage needs neither S nor the two products with it
 };
 
 // shared memory: LPC_TMA_NBUF tile buffers | full[NBUF], done[NBUF] mbarriers (64 bytes) | twiddles of the in-place
@@ -217,23 +219,38 @@ k_admm_cols_tma(FusedK f, ColsTmaK ck, int n_items, const typename CxT<T>::type*
             Dft<T, RL, -1>::run(v0);
             Dft<T, RL, -1>::run(v1);
             const C wj = Wj[j];
-            const C s0 = cx_mul(Sy0[j], sxv);
             const T k0 = fmaf(ck.mu2, gxv, ck.mu3);
+            if (ck.s_folded) {
 #pragma unroll
-            for (int m = 0; m < RL; ++m) {
-                const C Hv = Hh[m];
-                // R_divmat (admm.py:186-190) with |PsiTPsi| in closed form, times scale
-                const T gy = T(2) - T(2) * (wj.x * ck.cm[m] - wj.y * ck.sm[m]);
-                const T den = fmaf(ck.mu1, fmaf(Hv.x, Hv.x, Hv.y * Hv.y), fmaf(ck.mu2, gy, k0));
-                const T Rn = __fdividef(ck.scale, den);  // MUFU.RCP: 1 ulp is far inside the parity budget
-                const C S = cx_mul(s0, ck.sym[m]);
-                const C Hs = cx_mul(S, Hv);
-                C Hc = Hv; Hc.y = -Hc.y;
-                const C Hsa = cx_mul(S, Hc);
-                const C mm = cx_mul(Hsa, v1[m]);
-                C Vh; Vh.x = Rn * (v0[m].x - mm.x); Vh.y = Rn * (v0[m].y - mm.y);
-                v0[m] = Vh;
-                v1[m] = cx_mul(Hs, Vh);
+                for (int m = 0; m < RL; ++m) {
+                    const C Hs = Hh[m];  // S*H; |S*H|^2 = |H|^2
+                    const T gy = T(2) - T(2) * (wj.x * ck.cm[m] - wj.y * ck.sm[m]);
+                    const T den = fmaf(ck.mu1, fmaf(Hs.x, Hs.x, Hs.y * Hs.y), fmaf(ck.mu2, gy, k0));
+                    const T Rn = __fdividef(ck.scale, den);
+                    C Hsa = Hs; Hsa.y = -Hsa.y;  // S*conj(H) = conj(S*H) for real S
+                    const C mm = cx_mul(Hsa, v1[m]);
+                    C Vh; Vh.x = Rn * (v0[m].x - mm.x); Vh.y = Rn * (v0[m].y - mm.y);
+                    v0[m] = Vh;
+                    v1[m] = cx_mul(Hs, Vh);
+                }
+            } else {
+                const C s0 = cx_mul(Sy0[j], sxv);
+#pragma unroll
+                for (int m = 0; m < RL; ++m) {
+                    const C Hv = Hh[m];
+                    // R_divmat (admm.py:186-190) with |PsiTPsi| in closed form, times scale
+                    const T gy = T(2) - T(2) * (wj.x * ck.cm[m] - wj.y * ck.sm[m]);
+                    const T den = fmaf(ck.mu1, fmaf(Hv.x, Hv.x, Hv.y * Hv.y), fmaf(ck.mu2, gy, k0));
+                    const T Rn = __fdividef(ck.scale, den);  // MUFU.RCP: 1 ulp is far inside the parity budget
+                    const C S = cx_mul(s0, ck.sym[m]);
+                    const C Hs = cx_mul(S, Hv);
+                    C Hc = Hv; Hc.y = -Hc.y;
+                    const C Hsa = cx_mul(S, Hc);
+                    const C mm = cx_mul(Hsa, v1[m]);
+                    C Vh; Vh.x = Rn * (v0[m].x - mm.x); Vh.y = Rn * (v0[m].y - mm.y);
+                    v0[m] = Vh;
+                    v1[m] = cx_mul(Hs, Vh);
+                }
             }
             // H of this thread's next pair: in flight during the inverse butterflies
             const int gn = g + NTHG;
@@ -268,7 +285,8 @@ k_admm_cols_tma(FusedK f, ColsTmaK ck, int n_items, const typename CxT<T>::type*
 // kymap[pos] = frequency held at position pos after the forward passes (fft_ip_freq_of_pos), pos = j*RL + m.
 template <typename T>
 __global__ void k_tile_H_mid(const typename CxT<T>::type* __restrict__ H, const int* __restrict__ kymap,
-                             typename CxT<T>::type* __restrict__ Hm, int DC, int Hp, int Nh, int NT, int RL) {
+                             typename CxT<T>::type* __restrict__ Hm, int DC, int Hp, int Nh, int NT, int RL,
+                             const typename CxT<T>::type* __restrict__ Sy = nullptr, const typename CxT<T>::type* __restrict__ Sx = nullptr) {
     using C = typename CxT<T>::type;
     const int NBL = Hp / RL;
     const int64_t n = (int64_t)DC * NT * Hp * LPC_NCT;
@@ -282,7 +300,10 @@ __global__ void k_tile_H_mid(const typename CxT<T>::type* __restrict__ H, const 
         const int ky = kymap[j * RL + m];
         const int kx = tile * LPC_NCT + c;
         C h; h.x = h.y = T(0);
-        if (kx < Nh) h = H[((int64_t)q * Hp + ky) * Nh + kx];
+        if (kx < Nh) {
+            h = H[((int64_t)q * Hp + ky) * Nh + kx];
+            if (Sy != nullptr) h = cx_mul(cx_mul(Sy[ky], Sx[kx]), h);  // fold the (real, +-1) ifftshift phase: ColsTmaK::s_folded
+        }
         Hm[i] = h;
     }
 }

@@ -69,7 +69,7 @@ def finalize():
 
 
 def reconstruct_sharded(host_batch, psf, n_iter=100, algo="admm", chunk=1, gather=False, solver=None,
-                        reconstruct_fn=None, device=None, out=None, **solver_kw):
+                        reconstruct_fn=None, device=None, out=None, total=None, **solver_kw):
     """BASELINE configs[3] as a call: reconstruct ``host_batch`` ([N, Dd, h, w, C], host memory, the same tensor on
     every rank) with the batch axis sharded contiguously over the ranks of the job.
 
@@ -80,14 +80,19 @@ def reconstruct_sharded(host_batch, psf, n_iter=100, algo="admm", chunk=1, gathe
     ``[n_local, D, h, w, C]`` -- or, with ``gather=True``, ``(full, index_range)`` where ``full`` is the
     ``[N, D, h, w, C]`` result on every rank (one all_gather of the padded shards at the end).
 
+    ``total=N``: ``host_batch`` holds ONLY this rank's shard (``len(shard_batch(N, world, rank))`` measurements) of a global
+    batch of N -- a loader that reads per rank never materialises the whole batch on every rank.
     ``out`` is this rank's pre-allocated (pinned) ``[n_local, D, h, w, C]`` result buffer -- pinning gigabytes of host
     memory takes seconds, a caller that reconstructs batch after batch allocates it once.
     ``solver`` re-uses an existing solver object (its plans and CUDA graphs); ``reconstruct_fn(inputs, outputs)`` replaces
     the engine call (the CPU tests of the host logic run it under gloo with a stand-in)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    N = int(host_batch.shape[0])
+    N = int(host_batch.shape[0]) if total is None else int(total)
     mine = shard_batch(N, world, rank)
+    base = mine.start if total is None else 0  # index of this rank's first measurement inside host_batch
+    if total is not None:
+        assert int(host_batch.shape[0]) == len(mine), "with total=N, host_batch must hold exactly this rank's shard"
     D = int(psf.shape[0])
     h, w, C = (int(v) for v in host_batch.shape[2:])
     psf = broadcast_psf(psf, src=0)
@@ -106,7 +111,7 @@ def reconstruct_sharded(host_batch, psf, n_iter=100, algo="admm", chunk=1, gathe
         ins, outs = [], []
         for s in range(0, n_local, max(int(chunk), 1)):
             e = min(s + max(int(chunk), 1), n_local)
-            ins.append(pinned(host_batch[mine.start + s : mine.start + e].contiguous()))
+            ins.append(pinned(host_batch[base + s : base + e].contiguous()))
             outs.append(local_out[s:e])
         if reconstruct_fn is not None:
             reconstruct_fn(ins, outs)

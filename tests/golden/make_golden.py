@@ -137,6 +137,20 @@ def make_unrolled(lensless, torch):
             un._alpha_p = torch.nn.Parameter(torch.from_numpy(alpha).to(tdt))
             un._tk_p = torch.nn.Parameter(torch.from_numpy(tk).to(tdt))
             store[f"unrolled_fista_{tag}"] = un.forward(torch.from_numpy(batch).to(tdt)).numpy().copy()
+        # forward(batch, psfs): one PSF per sample; UnrolledFISTA keeps the CONSTRUCTOR PSF's initial value and step
+        # sizes (trainable_recon.py:347-350 swaps the convolver only; unrolled_fista.py:55-73)
+        psfs = np.stack([psf * (0.5 + rng.random(psf.shape)).astype(np.float32) for _ in range(3)])
+        store["psfs"] = psfs
+        un = lensless.UnrolledFISTA(torch.from_numpy(psf), n_iter=n, tk=1.5)
+        un._alpha_p = torch.nn.Parameter(torch.from_numpy(alpha).to(torch.float32))
+        un._tk_p = torch.nn.Parameter(torch.from_numpy(tk).to(torch.float32))
+        store["unrolled_fista_psfs_t32"] = un.forward(torch.from_numpy(batch), psfs=torch.from_numpy(psfs)).numpy().copy()
+        un = lensless.UnrolledADMM(torch.from_numpy(psf), n_iter=n)
+        un._mu1_p = torch.nn.Parameter(torch.from_numpy(mu1).to(torch.float32))
+        un._mu2_p = torch.nn.Parameter(torch.from_numpy(mu2).to(torch.float32))
+        un._mu3_p = torch.nn.Parameter(torch.from_numpy(mu3).to(torch.float32))
+        un._tau_p = torch.nn.Parameter(torch.from_numpy(tau).to(torch.float32))
+        store["unrolled_admm_psfs_t32"] = un.forward(torch.from_numpy(batch), psfs=torch.from_numpy(psfs)).numpy().copy()
         # defaults (constant parameters): must equal ADMM / a FISTA without the first-iteration aliasing
         un = lensless.UnrolledFISTA(torch.from_numpy(psf), n_iter=n)
         store["unrolled_fista_default_t32"] = un.forward(torch.from_numpy(batch)).numpy().copy()

@@ -70,6 +70,11 @@ def _worker_sharded(rank, world, port, out):
 
     full, mine = lpd.reconstruct_sharded(batch, psf, n_iter=3, chunk=2, gather=True, reconstruct_fn=fake_engine)
     local, mine2 = lpd.reconstruct_sharded(batch, psf, n_iter=3, chunk=3, gather=False, reconstruct_fn=fake_engine)
+    # the rank holds only its own shard of the global batch
+    shard = batch[mine[0] : mine[-1] + 1].clone()
+    local2, mine3 = lpd.reconstruct_sharded(shard, psf, n_iter=3, chunk=3, reconstruct_fn=fake_engine, total=7)
+    assert list(mine3) == list(mine) and torch.equal(local2, local)
+    calls.pop()
     out.put((rank, list(mine), full, local, calls, psf.sum().item()))
     lpd.finalize()
 

@@ -491,6 +491,21 @@ def test_unrolled_fista_forward_matches_reference():
     assert rel_to_max(out.cpu().numpy(), g["unrolled_fista_default_t32"]) <= TOL
 
 
+def test_unrolled_forward_with_per_sample_psfs_matches_reference():
+    """forward(batch, psfs=[B,...]) of the reference's unrolled solvers: per-sample convolver (and, for ADMM, R_divmat);
+    UnrolledFISTA keeps the constructor PSF's initial value and learned step sizes."""
+    g = load_golden("unrolled")
+    n = len(g["mu1"])
+    batch, psfs = dev(g["batch"]), dev(g["psfs"])
+    rec = L().UnrolledFISTA(dev(g["psf"]), n_iter=n, tk=1.5)
+    rec.set_parameters(alpha=g["alpha"], tk=g["tk"])
+    out = rec.forward(batch, psfs=psfs)
+    assert rel_to_max(out.cpu().numpy(), g["unrolled_fista_psfs_t32"]) <= TOL, rel_to_max(out.cpu().numpy(), g["unrolled_fista_psfs_t32"])
+    rec = L().UnrolledADMM(dev(g["psf"]), n_iter=n, mu1=g["mu1"], mu2=g["mu2"], mu3=g["mu3"], tau=g["tau"])
+    out = rec.forward(batch, psfs=psfs)
+    assert rel_to_max(out.cpu().numpy(), g["unrolled_admm_psfs_t32"]) <= TOL, rel_to_max(out.cpu().numpy(), g["unrolled_admm_psfs_t32"])
+
+
 def test_unrolled_rejects_processors_and_long_runs():
     g = load_golden("unrolled")
     with pytest.raises(NotImplementedError):
