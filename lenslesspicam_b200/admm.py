@@ -135,8 +135,16 @@ def finite_diff_gram(shape, dtype=None, is_torch=True, device=None):
     return out
 
 
-def apply_admm(psf, data, n_iter, verbose=False, **kwargs):
-    """admm.py:400-419 with tensors instead of file paths (loading images is the reference's job)."""
+def apply_admm(psf_fp, data_fp, n_iter, verbose=False, **kwargs):
+    """admm.py:400-419.  ``psf_fp`` / ``data_fp`` are file paths as in the reference (loaded by the GPU loader,
+    ``lenslesspicam_b200.io.load_data``, with ``**kwargs``) or already-loaded CUDA tensors."""
+    if isinstance(psf_fp, str):
+        from .io import load_data
+
+        psf, data = load_data(psf_fp=psf_fp, data_fp=data_fp, plot=False, **kwargs)
+        kwargs = {}
+    else:
+        psf, data = psf_fp, data_fp
     recon = ADMM(psf, n_iter=n_iter, **kwargs)
     recon.set_data(data)
     torch.cuda.synchronize()

@@ -116,12 +116,20 @@ class FISTA(GradientDescent):
         self._tk = self._initial_tk
 
 
-def apply_gradient_descent(psf, data, n_iter, verbose=False, proj=non_neg, **kwargs):
-    """gd.py:244-263 with tensors instead of file paths (loading images is ``lenslesspicam_b200.io``'s job)."""
+def apply_gradient_descent(psf_fp, data_fp, n_iter, verbose=False, proj=non_neg, **kwargs):
+    """gd.py:244-263.  ``psf_fp`` / ``data_fp`` are file paths as in the reference (loaded by the GPU loader,
+    ``lenslesspicam_b200.io.load_data``, with ``**kwargs``) or already-loaded CUDA tensors."""
     import time
 
     import torch
 
+    if isinstance(psf_fp, str):
+        from .io import load_data
+
+        psf, data = load_data(psf_fp=psf_fp, data_fp=data_fp, plot=False, **kwargs)
+        kwargs = {}
+    else:
+        psf, data = psf_fp, data_fp
     recon = GradientDescent(psf, n_iter=n_iter, proj=proj, **kwargs)
     recon.set_data(data)
     torch.cuda.synchronize()

@@ -84,3 +84,15 @@ def test_loaded_data_reconstructs_like_the_reference_inputs():
     out = rec.apply(n_iter=10, disp_iter=None, plot=False).cpu().numpy()
     ref = orc.reconstruct("admm", g["real_ds4_psf"], g["real_ds4_data"], 10)
     assert rel_to_max(out, ref) <= 1e-5
+
+
+def test_apply_admm_and_apply_gradient_descent_take_file_paths():
+    """admm.py:400-419 / gd.py:244-263: the reference's one-call helpers load the files themselves"""
+    import lensless_oracle as orc
+    import lenslesspicam_b200 as L
+
+    g = load_golden("loader")
+    res = L.apply_admm(fp("real_psf_crop"), fp("real_data_crop"), 5, downsample=4, normalize=True)
+    assert rel_to_max(res.cpu().numpy(), orc.reconstruct("admm", g["real_ds4_psf"], g["real_ds4_data"], 5)) <= 1e-5
+    res = L.apply_gradient_descent(fp("real_psf_crop"), fp("real_data_crop"), 5, downsample=4, normalize=True)
+    assert rel_to_max(res.cpu().numpy(), orc.reconstruct("gd", g["real_ds4_psf"], g["real_ds4_data"], 5)) <= 1e-5

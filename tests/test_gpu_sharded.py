@@ -72,3 +72,23 @@ def test_sharded_batch_equals_single_gpu_bit_for_bit(tmp_path):
         assert np.array_equal(d["local"], single[d["mine"]])
         seen += list(d["mine"])
     assert seen == list(range(batch.shape[0]))
+
+
+def test_engine_calls_leave_the_current_device_alone():
+    """every C-ABI entry point runs on the plan's device and restores the caller's: a solver living on
+    cuda:1 must not re-target torch's current device"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import lenslesspicam_b200 as L
+
+    torch.cuda.set_device(0)
+    psf, batch = _problem(n=1)
+    rec = L.ADMM(psf.to("cuda:1"), n_iter=5)
+    rec.set_data(batch[0].to("cuda:1"))
+    out = rec.apply(disp_iter=None, plot=False)
+    assert out.device == torch.device("cuda", 1)
+    assert torch.cuda.current_device() == 0
+    ref = L.ADMM(psf.to("cuda:0"), n_iter=5)
+    ref.set_data(batch[0].to("cuda:0"))
+    assert torch.equal(ref.apply(disp_iter=None, plot=False).cpu(), out.cpu())
+    assert torch.zeros(1, device="cuda").device.index == 0
