@@ -115,6 +115,9 @@ int lpc_geometry(int h, int w, int* Hp, int* Wp, int* start_y, int* start_x);
 int lpc_plan_create(lpc_plan_t* out, int device, int algo, int dtype, int norm, int B, int D,
                     int C, int h, int w, int flags);
 int lpc_plan_destroy(lpc_plan_t plan);
+/* Does this library's compiled menu of the fused engine hold the padded row length Wp / column length Hp?  (A size
+ * outside it runs the cuFFT engine; the Python mirror compiles a size-specific library on demand instead.) */
+int lpc_menu_query(int Wp, int Hp, int* has_rows, int* has_cols);
 
 /* RealFFTConvolve2D.set_psf (rfft_convolve.py:102-131): pad PSF, H = rfft2(.)*norm,
  * plus the algorithm constants derived from H: ADMM R_divmat (admm.py:186-190),

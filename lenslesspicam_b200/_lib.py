@@ -42,6 +42,7 @@ PROTOTYPES = {
     "lpc_geometry": (_i, [_i, _i, _ip, _ip, _ip, _ip]),
     "lpc_plan_create": (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "lpc_plan_destroy": (_i, [_vp]),
+    "lpc_menu_query": (_i, [_i, _i, _ip, _ip]),
     "lpc_set_psf": (_i, [_vp, _vp, _vp]),
     "lpc_set_admm_params": (_i, [_vp, _d, _d, _d, _d, _vp]),
     "lpc_set_gd_params": (_i, [_vp, _d, _d, _d, _vp]),

@@ -1880,6 +1880,12 @@ int lpc_plan_create(lpc_plan_t* out, int device, int algo, int dtype, int norm, 
     return LPC_OK;
 }
 
+int lpc_menu_query(int Wp, int Hp, int* has_rows, int* has_cols) {
+    if (has_rows) *has_rows = find_rows(Wp) ? 1 : 0;
+    if (has_cols) *has_cols = find_cols(Hp) ? 1 : 0;
+    return LPC_OK;
+}
+
 int lpc_plan_destroy(lpc_plan_t plan) {
     if (!plan) return LPC_OK;
     DeviceGuard guard(plan->device);

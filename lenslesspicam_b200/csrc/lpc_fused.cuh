@@ -45,6 +45,23 @@ constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIAN
 // 2048x1536 / 1024x768 / 512x384: the bundled 3040x4056 data at downsample 4 / 8 / 16; the small ones are the shapes of tests/golden (odd, mixed, gray).
 // Round 2 widened the menu to the padded sizes next_fast_len(2d-1) of the usual sensor / dataset dimensions d (64 ... 4056):
 // rows and columns are instantiated independently, so any combination of a row size and a column size is served.
+// On-demand specialisation (lenslesspicam_b200/_lib.py::load_for): a padded size outside the menu is compiled into its own
+// small library by nvcc at first use -- only the two extra entries: -DLPC_MENU_ONLY_EXTRA -DLPC_HAVE_MENU_EXTRA_H with a
+// generated lpc_menu_extra.h on the include path that defines LPC_ROW_MENU_EXTRA(X) / LPC_COL_MENU_EXTRA(X) (nvcc
+// splits -D values at commas, so the entries cannot ride on the command line) -- and cached next to liblpc.so.
+#ifdef LPC_HAVE_MENU_EXTRA_H
+#include "lpc_menu_extra.h"
+#endif
+#ifndef LPC_ROW_MENU_EXTRA
+#define LPC_ROW_MENU_EXTRA(X)
+#endif
+#ifndef LPC_COL_MENU_EXTRA
+#define LPC_COL_MENU_EXTRA(X)
+#endif
+#ifdef LPC_MENU_ONLY_EXTRA
+#define LPC_ROW_MENU(X) LPC_ROW_MENU_EXTRA(X)
+#define LPC_COL_MENU(X) LPC_COL_MENU_EXTRA(X)
+#else
 #define LPC_ROW_MENU(X) \
     X(4096, 16, 16, 16) X(3840, 15, 16, 16) X(3200, 10, 16, 10, 2) \
     X(3072, 12, 16, 16) X(2880, 15, 16, 12) X(2560, 10, 16, 16) X(2400, 15, 16, 10) X(2160, 15, 16, 9) X(2048, 16, 16, 8) \
@@ -52,7 +69,8 @@ constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIAN
     X(1080, 15, 9, 8) X(1024, 16, 16, 4) X(960, 15, 16, 4) X(800, 5, 16, 10) X(768, 3, 16, 16) X(720, 15, 16, 3) X(640, 5, 16, 8) \
     X(600, 15, 8, 5) X(540, 15, 9, 4) X(512, 16, 8, 4) X(480, 15, 16, 2) X(400, 5, 16, 5) X(384, 3, 16, 8) X(360, 15, 8, 3) \
     X(320, 5, 16, 4) X(288, 9, 16, 2) X(270, 15, 9, 2) X(256, 16, 16) X(240, 15, 16) X(200, 5, 8, 5) X(128, 16, 8) X(125, 5, 5, 5) \
-    X(75, 15, 5) X(64, 16, 4) X(54, 9, 6)
+    X(75, 15, 5) X(64, 16, 4) X(54, 9, 6) \
+    LPC_ROW_MENU_EXTRA(X)
 // (column sequences end in a small radix: that pass is fused with the spectral update in registers)
 #define LPC_COL_MENU(X) \
     X(4096, 16, 16, 4, 4) X(3840, 16, 16, 5, 3) X(3200, 16, 10, 5, 4) \
@@ -61,7 +79,9 @@ constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIAN
     X(1080, 8, 15, 9) X(1024, 16, 16, 4) X(960, 15, 16, 4) X(800, 16, 10, 5) X(768, 16, 16, 3) X(720, 15, 16, 3) X(640, 16, 8, 5) \
     X(600, 15, 8, 5) X(540, 4, 15, 9) X(512, 16, 8, 4) X(480, 15, 8, 4) X(405, 15, 9, 3) X(400, 16, 5, 5) X(384, 16, 8, 3) \
     X(360, 15, 8, 3) X(320, 16, 5, 4) X(270, 15, 9, 2) X(256, 16, 16) X(240, 15, 16) X(200, 5, 8, 5) X(128, 16, 8) X(48, 16, 3) \
-    X(45, 15, 3) X(40, 5, 8) X(27, 9, 3)
+    X(45, 15, 3) X(40, 5, 8) X(27, 9, 3) \
+    LPC_COL_MENU_EXTRA(X)
+#endif
 
 struct FusedK {
     int Hp, Wp, Nh, NT;  // NT tiles of LPC_NCT columns cover Nh = Wp/2+1

@@ -169,8 +169,13 @@ class ReconstructionAlgorithm(abc.ABC):
             plan = ctypes.c_void_p()
             D, h, w, C = (int(v) for v in self._psf.shape)
             flags = self._flags | (_lib.FLAG_PSF_PER_SAMPLE if per_sample else 0)
+            creator = lib
+            if self._dtype == torch.float32 and not (flags & (_lib.FLAG_ENGINE_V1 | _lib.FLAG_PNP)):
+                from . import _jit  # a padded size outside the compiled menu gets its own specialised library
+
+                creator = _jit.library_for(self._padded_shape[2], self._padded_shape[1])
             _lib.check(
-                lib.lpc_plan_create(
+                creator.lpc_plan_create(
                     ctypes.byref(plan), self._dev_index, self._ALGO, torch_dtype_code(self._dtype),
                     _lib.NORMS[self._norm], B, D, C, h, w, flags,
                 )

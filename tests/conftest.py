@@ -11,6 +11,10 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# padded sizes outside the compiled menu are compiled on demand by nvcc (lenslesspicam_b200/_jit.py, ~15 s each); the
+# suite keeps that off -- such shapes run the cuFFT engine -- except in the test that exercises it
+os.environ.setdefault("LPC_JIT", "0")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")

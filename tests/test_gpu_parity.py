@@ -7,6 +7,8 @@ Tolerance (north_star): 1e-5 relative for fp32 -- measured as max|ours-ref| / ma
 pad/crop indexing bit-exact.  FISTA at large iteration counts is gated on the
 fp64 envelope instead: err(ours, fp64) <= 1.5 * err(ref fp32, fp64).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -664,3 +666,30 @@ def test_every_menu_size_runs_the_fused_engine_and_agrees_with_the_cufft_engine(
             assert rel_to_max(a.cpu().numpy(), orc.reconstruct(algo, psf, data, n)) <= TOL, (shape, algo)
         del ra, rb
     torch.cuda.empty_cache()
+
+
+def test_on_demand_specialisation_of_a_size_outside_the_menu(monkeypatch):
+    """a padded size outside the compiled menu no longer loses the fused engine -- the first solver
+    of that size compiles its two template instantiations with nvcc (lenslesspicam_b200/_jit.py) and runs engine v2;
+    with LPC_JIT=0 (or no nvcc) the cuFFT engine serves it and the mirror warns."""
+    import shutil
+    import warnings
+
+    import lenslesspicam_b200.recon as recon_mod
+
+    h, w = 125, 63  # padded 250 x 125: row length 125 is in the menu, column length 250 is not
+    psf, data = orc.synthetic_problem(h, w, 3, seed=3)
+    monkeypatch.setenv("LPC_JIT", "0")
+    recon_mod.ReconstructionAlgorithm._warned_v1 = False
+    with warnings.catch_warnings(record=True) as rec_w:
+        warnings.simplefilter("always")
+        a, ra = run("admm", psf, data, 10)
+    assert _engine_version(ra) == 1 and any("compiled menu" in str(x.message) for x in rec_w)
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available: the on-demand build cannot run here")
+    monkeypatch.setenv("LPC_JIT", "1")
+    for algo in ("admm", "fista"):
+        b, rb = run(algo, psf, data, 10)
+        assert _engine_version(rb) == 2, algo
+        assert rel_to_max(b.cpu().numpy(), orc.reconstruct(algo, psf, data, 10)) <= TOL, algo
+    assert rel_to_max(a.cpu().numpy(), run("admm", psf, data, 10)[0].cpu().numpy()) <= 3e-6
