@@ -189,7 +189,8 @@ class ReconstructionAlgorithm(abc.ABC):
                 _, Hp, Wp, _ = self._padded_shape
                 warnings.warn(
                     f"lenslesspicam_b200: padded size {Hp}x{Wp} is not in the fused engine's compiled menu "
-                    "(csrc/lpc_fused.cuh: LPC_ROW_MENU / LPC_COL_MENU); this solver runs the cuFFT-based engine v1, "
+                    "(csrc/lpc_fused.cuh: LPC_ROW_MENU / LPC_COL_MENU) and could not be compiled on demand (LPC_JIT=0, no nvcc, or "
+                    "more than four radix passes); this solver runs the cuFFT-based engine v1, "
                     "about 2x slower.  `engine_version` on the solver reports which engine serves it.",
                     RuntimeWarning, stacklevel=3,
                 )
