@@ -127,46 +127,87 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
                 fft_bfly_load<T, RL>(W, 0, 1, PI, Wp, j, v[it]);
                 fft_bfly_compute<T, RL, +1>(v[it], twI + TR::tw_off_last, NSL, j);
             }
+            if constexpr (MODE == LPC_GD_INIT || MODE == LPC_GD_RESID) {
 #pragma unroll
-            for (int m = 0; m < RL; ++m) {
-                const int col = j + m * NSL - sx;  // window column of padded pixel j + m*NSL
-                C z; z.x = T(0); z.y = T(0);       // everything outside the window is the zero padding
-                if (col >= 0 && col < w) {
-                    if (MODE == LPC_GD_INIT) {
-                        z.x = x[ia + col];
-                        if (has_b) z.y = x[ib + col];
-                    } else if (MODE == LPC_GD_RESID) {
-                        z.x = v[it][m].x - dpl[(int64_t)ra * w + col];  // crop(Hx) - y   (gd.py:129)
-                        if (has_b) z.y = v[it][m].y - dpl[(int64_t)rb * w + col];
-                    } else {
+                for (int m = 0; m < RL; ++m) {
+                    const int col = j + m * NSL - sx;  // window column of padded pixel j + m*NSL
+                    C z; z.x = T(0); z.y = T(0);       // everything outside the window is the zero padding
+                    if (col >= 0 && col < w) {
+                        if (MODE == LPC_GD_INIT) {
+                            z.x = x[ia + col];
+                            if (has_b) z.y = x[ib + col];
+                        } else {
+                            z.x = v[it][m].x - dpl[(int64_t)ra * w + col];  // crop(Hx) - y   (gd.py:129)
+                            if (has_b) z.y = v[it][m].y - dpl[(int64_t)rb * w + col];
+                        }
+                    }
+                    v[it][m] = z;
+                }
+            } else {
+                // update modes read AND write x / mom: a load that follows a store to the same array cannot be hoisted
+                // above it, so an element-by-element loop exposes one global-load latency per element (ncu, round 2: 48 %
+                // of the kernel's samples on the long scoreboard).  Elements are therefore handled in chunks: all loads of
+                // a chunk, then its arithmetic and stores -- gd_rows(update) 83 -> 66 us, FISTA-300 12.5 -> 13.4 recon/s.
+                // (The same batching of SHARED-memory reads ahead of stores in the gather / separation loops was measured
+                // slower -- B2 205 -> 226 us -- and is not used: there the interleaving feeds the LSU more evenly.)
+                constexpr int CH = 4;
 #pragma unroll
-                        for (int s = 0; s < 2; ++s) {
-                            if (s == 1 && !has_b) break;
-                            const int64_t o = (s == 0 ? ia : ib) + col;
-                            const T gs = (s == 0) ? v[it][m].x : v[it][m].y;
-                            T xn;
-                            if (MODE == LPC_GD_UPD_GD) {  // gd.py:132-134
-                                const T u = x[o] - alpha * gs;
-                                xn = u > T(0) ? u : T(0);
-                            } else if (MODE == LPC_GD_UPD_NESTEROV) {  // gd.py:183-188
-                                const T p_prev = mom[o];
-                                const T p_new = scalar * p_prev - alpha * gs;
-                                mom[o] = p_new;
-                                const T u = x[o] + (-scalar * p_prev + (T(1) + scalar) * p_new);
-                                xn = u > T(0) ? u : T(0);
-                            } else {  // FISTA, gd.py:235-241
-                                const T zz = x[o] - alpha * gs;
-                                const T xk = zz > T(0) ? zz : T(0);
-                                const T prev = first ? zz : mom[o];
-                                mom[o] = xk;
-                                xn = xk + scalar * (xk - prev);
+                for (int m0 = 0; m0 < RL; m0 += CH) {
+                    T xv[CH][2], pv[CH][2];
+#pragma unroll
+                    for (int mm = 0; mm < CH; ++mm) {
+                        const int m = m0 + mm;
+                        xv[mm][0] = xv[mm][1] = pv[mm][0] = pv[mm][1] = T(0);
+                        if (m < RL) {
+                            const int col = j + m * NSL - sx;
+                            if (col >= 0 && col < w) {
+                                xv[mm][0] = x[ia + col];
+                                if (has_b) xv[mm][1] = x[ib + col];
+                                if (MODE == LPC_GD_UPD_NESTEROV || (MODE == LPC_GD_UPD_FISTA && !first)) {
+                                    pv[mm][0] = mom[ia + col];
+                                    if (has_b) pv[mm][1] = mom[ib + col];
+                                }
                             }
-                            x[o] = xn;
-                            if (s == 0) z.x = xn; else z.y = xn;
+                        }
+                    }
+#pragma unroll
+                    for (int mm = 0; mm < CH; ++mm) {
+                        const int m = m0 + mm;
+                        if (m < RL) {
+                            const int col = j + m * NSL - sx;
+                            C z; z.x = T(0); z.y = T(0);
+                            if (col >= 0 && col < w) {
+#pragma unroll
+                                for (int s = 0; s < 2; ++s) {
+                                    if (s == 1 && !has_b) break;
+                                    const int64_t o = (s == 0 ? ia : ib) + col;
+                                    const T gs = (s == 0) ? v[it][m].x : v[it][m].y;
+                                    const T xo = xv[mm][s];
+                                    T xn;
+                                    if (MODE == LPC_GD_UPD_GD) {  // gd.py:132-134
+                                        const T u = xo - alpha * gs;
+                                        xn = u > T(0) ? u : T(0);
+                                    } else if (MODE == LPC_GD_UPD_NESTEROV) {  // gd.py:183-188
+                                        const T p_prev = pv[mm][s];
+                                        const T p_new = scalar * p_prev - alpha * gs;
+                                        mom[o] = p_new;
+                                        const T u = xo + (-scalar * p_prev + (T(1) + scalar) * p_new);
+                                        xn = u > T(0) ? u : T(0);
+                                    } else {  // FISTA, gd.py:235-241
+                                        const T zz = xo - alpha * gs;
+                                        const T xk = zz > T(0) ? zz : T(0);
+                                        const T prev = first ? zz : pv[mm][s];
+                                        mom[o] = xk;
+                                        xn = xk + scalar * (xk - prev);
+                                    }
+                                    x[o] = xn;
+                                    if (s == 0) z.x = xn; else z.y = xn;
+                                }
+                            }
+                            v[it][m] = z;
                         }
                     }
                 }
-                v[it][m] = z;
             }
             Dft<T, RL, -1>::run(v[it]);  // first pass of the reversed sequence: Ns = 1, no twiddles
         }
