@@ -70,12 +70,17 @@ def plan_cols(N):
         seq = seq[:-1] + list(split)
         if len(seq) > 4:
             return None
-    odd = [r for r in seq[:-1] if r % 2]
+    head, last = seq[:-1], seq[-1]
+    even = [r for r in head if r % 2 == 0]
+    if len(even) == 1 and last % 2 and len(head) >= 2:
+        # one radix carries every factor of two: first, so that the two outer passes run warp-locally (lpc_fft.cuh: IpWl)
+        head.remove(even[0])
+        return [even[0]] + head + [last]
+    odd = [r for r in head if r % 2]
     if odd:
         o = max(odd)
-        head = seq[:-1]
         head.remove(o)
-        seq = [o] + head + [seq[-1]]
+        seq = [o] + head + [last]
     return seq
 
 

@@ -91,7 +91,10 @@ using ColsTmaKern = void (*)(FusedK, ColsTmaK, int, const float2*, const float2*
                              const float2*);
 // threads per compute group of the persistent column kernel: two groups of 288 (measured at Hp = 2160, A per launch:
 // 1x960 232 us, 2x480 175, 3x288 without a look-ahead buffer 160, 2x384 155, 2x288 147 -- 96 registers, no spills)
-constexpr int LPC_TMA_NG = 2, LPC_TMA_NTHG = 288;
+#ifndef LPC_TMA_NTHG_DEF
+#define LPC_TMA_NTHG_DEF 288
+#endif
+constexpr int LPC_TMA_NG = 2, LPC_TMA_NTHG = LPC_TMA_NTHG_DEF;
 using GdColsTmaKern = void (*)(GdFusedK, int, const float2*, float2*, const float2*);
 struct ColsEntry { int N, npass, radix[4]; ColsKern kern[2]; GdColsKern gd; ColsTmaKern tma; GdColsTmaKern gd_tma; };
 template <int... Rs> constexpr int seq_len() { return (int)sizeof...(Rs); }

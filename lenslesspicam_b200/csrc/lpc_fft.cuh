@@ -200,15 +200,27 @@ LPC_HD void fft_bfly_store(typename CxT<T>::type* sm, int base, int es, int pads
 // tw = this pass's table [(k1-1)*S + n2] = exp(-2*pi*i*n2*k1/M) (conjugated for DIR > 0); a pass
 // with S == 1 has no twiddles.  After all DIF passes position p holds frequency fft_ip_freq_of_pos(p).
 // ----------------------------------------------------------------------------------------
-template <typename T, int R, int DIR, bool DIF>
-LPC_HD void fft_ip_bfly(typename CxT<T>::type* sm, int es, int M, int j, const typename CxT<T>::type* tw) {
+// WIN (outermost pass of a zero-padded transform whose non-zero elements are lo <= index < hi): a DIF butterfly takes
+// the elements outside the window as zeros WITHOUT reading them (the buffer need not be zero-filled), a DIT butterfly
+// does not store the outputs outside the window (nobody reads them).
+template <typename T, int R, int DIR, bool DIF, bool WIN = false>
+LPC_HD void fft_ip_bfly(typename CxT<T>::type* sm, int es, int M, int j, const typename CxT<T>::type* tw, int lo = 0, int hi = 0) {
     using C = typename CxT<T>::type;
     const int S = M / R;
     const int blk = j / S, n2 = j - blk * S;
-    C* p = sm + (blk * M + n2) * es;
+    const int e0 = blk * M + n2;
+    C* p = sm + e0 * es;
     C v[R];
 #pragma unroll
-    for (int m = 0; m < R; ++m) v[m] = p[m * S * es];
+    for (int m = 0; m < R; ++m) {
+        if (WIN && DIF) {
+            const int e = e0 + m * S;
+            v[m].x = v[m].y = T(0);
+            if (e >= lo && e < hi) v[m] = p[m * S * es];
+        } else {
+            v[m] = p[m * S * es];
+        }
+    }
     if (DIF) Dft<T, R, DIR>::run(v);
     if (S > 1) {
 #pragma unroll
@@ -220,7 +232,14 @@ LPC_HD void fft_ip_bfly(typename CxT<T>::type* sm, int es, int M, int j, const t
     }
     if (!DIF) Dft<T, R, DIR>::run(v);
 #pragma unroll
-    for (int m = 0; m < R; ++m) p[m * S * es] = v[m];
+    for (int m = 0; m < R; ++m) {
+        if (WIN && !DIF) {
+            const int e = e0 + m * S;
+            if (e >= lo && e < hi) p[m * S * es] = v[m];
+        } else {
+            p[m * S * es] = v[m];
+        }
+    }
 }
 
 // frequency index held at position p after the forward (DIF) passes with radices r[0..npass)
@@ -313,6 +332,30 @@ __device__ __forceinline__ void cta_fft_static_butfirst(typename CxT<T>::type* s
     if constexpr (sizeof...(Rest) > 0) cta_fft_static_passes<T, DIR, NB, NTH, PADSH, N, R0, 0, Rest...>(sm, tw, tid);
 }
 
+// ---- the FIRST Stockham pass (Ns = 1, no twiddles) with its input produced by a functor ld(i) -> element i instead of
+//      read from the transform buffer: the caller's gather / expansion stage feeds the butterflies directly and one
+//      shared-memory round trip of the row (and its barrier) disappears.  The outputs are written to sm right away: the
+//      caller guarantees that nobody still reads sm (its previous use ended at a barrier).  Ends with a barrier.
+template <typename T, int R, int DIR, int NTH, int PADSH, int N, typename LD>
+__device__ __forceinline__ void cta_fft_static_first_pass_ld(typename CxT<T>::type* sm, int tid, LD ld) {
+    using C = typename CxT<T>::type;
+    constexpr int nb = N / R;
+#pragma unroll 1
+    for (int j = tid; j < nb; j += NTH) {
+        C v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = ld(j + m * nb);
+        Dft<T, R, DIR>::run(v);
+        fft_bfly_store<T, R>(sm, 0, 1, PADSH, 1, j, v);
+    }
+    __syncthreads();
+}
+// passes 2 .. npass-1 of a sequence (everything between the first and the last)
+template <typename T, int DIR, int NB, int NTH, int PADSH, int N, int R0, int... Rest>
+__device__ __forceinline__ void cta_fft_static_mid(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid) {
+    if constexpr (sizeof...(Rest) > 1) cta_fft_static_butlast<T, DIR, NB, NTH, PADSH, N, R0, 0, Rest...>(sm, tw, tid);
+}
+
 template <int... Rs> struct IntList {};
 template <typename Acc, int... Rs> struct RevList;
 template <int... Acc> struct RevList<IntList<Acc...>> { using type = IntList<Acc...>; };
@@ -338,6 +381,15 @@ template <int N_, int... Rs> struct SeqTraits<FftSeq<N_, Rs...>> {
     static __device__ __forceinline__ void run_butlast(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid) {
         cta_fft_static_butlast<T, DIR, NB, NTH, Seq::padsh, N_, 1, 0, Rs...>(sm, tw, tid);
     }
+    static constexpr int first = Seq::radix[0];
+    template <typename T, int DIR, int NTH, typename LD>
+    static __device__ __forceinline__ void run_first_ld(typename CxT<T>::type* sm, int tid, LD ld) {
+        cta_fft_static_first_pass_ld<T, Seq::radix[0], DIR, NTH, Seq::padsh, N_, LD>(sm, tid, ld);
+    }
+    template <typename T, int DIR, int NB, int NTH>
+    static __device__ __forceinline__ void run_mid(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid) {
+        cta_fft_static_mid<T, DIR, NB, NTH, Seq::padsh, N_, Rs...>(sm, tw, tid);
+    }
     template <typename T, int DIR, int NB, int NTH>
     static __device__ __forceinline__ void run_butfirst(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid) {
         cta_fft_static_butfirst<T, DIR, NB, NTH, Seq::padsh, N_, Rs...>(sm, tw, tid);
@@ -360,36 +412,108 @@ template <int COUNT> struct BarNamed {
 };
 
 // ---- one in-place pass walked by NTH threads over NB interleaved transforms of length N
-template <typename T, int R, int DIR, bool DIF, int NB, int NTH, int N, int M>
-__device__ __forceinline__ void cta_fft_ip_pass(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid) {
+// (Measured and dropped, round 2: a butterfly that takes TWO adjacent transforms with 16-byte accesses and shared twiddle
+// loads -- half the shared-memory instructions of the outer passes -- made kernel A slower, 140.6 -> 143.8 us without
+// spills at 2 x 192 threads and 149-155 us with the spills of 2 x 288: the kernel wants more independent warps, not
+// fewer instructions.  profiles/README.md.)
+template <typename T, int R, int DIR, bool DIF, int NB, int NTH, int N, int M, bool WIN = false>
+__device__ __forceinline__ void cta_fft_ip_pass(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, int lo = 0, int hi = 0) {
     constexpr int total = (N / R) * NB;
 #pragma unroll 1
     for (int g = tid; g < total; g += NTH) {
         const int b = g % NB, j = g / NB;
-        fft_ip_bfly<T, R, DIR, DIF>(sm + b, NB, M, j, tw);
+        fft_ip_bfly<T, R, DIR, DIF, WIN>(sm + b, NB, M, j, tw, lo, hi);
     }
 }
 // forward: all DIF passes but the last (radix R_last, S = 1, no twiddles -- the caller fuses it with its
 // element-wise stage); a barrier separates consecutive passes, NONE follows the last one: the caller issues
 // whatever it wants in flight across that barrier (prefetches), then syncs itself
-template <typename T, int DIR, int NB, int NTH, int N, int M, int TWOFF, bool FIRST, typename BAR, int R, int... Rest>
-__device__ __forceinline__ void cta_fft_ip_dif_butlast(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
+template <typename T, int DIR, int NB, int NTH, int N, int M, int TWOFF, bool FIRST, bool WIN, typename BAR, int R, int... Rest>
+__device__ __forceinline__ void cta_fft_ip_dif_butlast(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar, int lo = 0, int hi = 0) {
     if constexpr (sizeof...(Rest) > 0) {
         if constexpr (!FIRST) bar.sync();
-        cta_fft_ip_pass<T, R, DIR, true, NB, NTH, N, M>(sm, tw + TWOFF, tid);
-        cta_fft_ip_dif_butlast<T, DIR, NB, NTH, N, M / R, TWOFF + (R - 1) * (M / R), false, BAR, Rest...>(sm, tw, tid, bar);
+        cta_fft_ip_pass<T, R, DIR, true, NB, NTH, N, M, (FIRST && WIN)>(sm, tw + TWOFF, tid, lo, hi);
+        cta_fft_ip_dif_butlast<T, DIR, NB, NTH, N, M / R, TWOFF + (R - 1) * (M / R), false, false, BAR, Rest...>(sm, tw, tid, bar);
     }
 }
 // inverse: all DIT passes but the innermost (the caller has done it), innermost first; a barrier
 // PRECEDES every pass (so the first one also orders the caller's stage before the first pass)
-template <typename T, int DIR, int NB, int NTH, int N, int M, int TWOFF, typename BAR, int R, int... Rest>
-__device__ __forceinline__ void cta_fft_ip_dit_butinner(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
+template <typename T, int DIR, int NB, int NTH, int N, int M, int TWOFF, bool WIN, typename BAR, int R, int... Rest>
+__device__ __forceinline__ void cta_fft_ip_dit_butinner(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar, int lo = 0, int hi = 0) {
     if constexpr (sizeof...(Rest) > 0) {
-        cta_fft_ip_dit_butinner<T, DIR, NB, NTH, N, M / R, TWOFF + (R - 1) * (M / R), BAR, Rest...>(sm, tw, tid, bar);
+        cta_fft_ip_dit_butinner<T, DIR, NB, NTH, N, M / R, TWOFF + (R - 1) * (M / R), false, BAR, Rest...>(sm, tw, tid, bar);
         bar.sync();
-        cta_fft_ip_pass<T, R, DIR, false, NB, NTH, N, M>(sm, tw + TWOFF, tid);
+        cta_fft_ip_pass<T, R, DIR, false, NB, NTH, N, M, WIN>(sm, tw + TWOFF, tid, lo, hi);
     }
 }
+
+// ---- the two OUTERMOST in-place passes without a group barrier between them.
+// DIF pass 1 (radix R1, stride S1 = N/R1) butterfly n2 writes the elements n2 + m*S1; DIF pass 2 (radix R2 inside the
+// blocks of M1 = N/R1, stride S2 = M1/R2) butterfly (blk, n2') reads blk*M1 + n2' + m*S2 -- all produced by the pass-1
+// butterflies of the residue CLASS n2 = n2' (mod S2).  A team of TS lanes of ONE warp therefore takes a class through
+// both passes (R2 butterflies of pass 1, __syncwarp, R1 butterflies of pass 2, per interleaved transform), and the S2
+// classes are independent of each other: the 9-warp compute group of the column kernels no longer meets at a named
+// barrier between these passes (ncu, round 2: 18 % of kernel A's stall samples sat on those barriers); the DIT
+// inverse mirrors it.  Lanes of a team: b = lane % NB (transform), idx = lane / NB (+ TS/NB per round).  Conflict-free
+// shared-memory accesses need the lane strides S2 and M1 (in 8*NB-byte granules) to be odd, which holds when R1
+// carries every factor of two of N (2160 = 16 * 135): only such sequences take this path (ip_warplocal_ok).
+#ifndef LPC_IP_WARPLOCAL
+#define LPC_IP_WARPLOCAL 1
+#endif
+template <int N, int NB, int NTH, int R1, int R2> struct IpWl {
+    static constexpr int M1 = N / R1, S2 = M1 / R2;
+    static constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+    static constexpr int cost(int ts) {  // butterfly rounds of a warp for both passes with teams of ts lanes
+        return (ts % NB != 0 || ts < NB) ? (1 << 30) : cdiv(S2, (NTH / 32) * (32 / ts)) * (cdiv(R2, ts / NB) + cdiv(R1, ts / NB));
+    }
+    static constexpr int TS = cost(32) <= cost(16) ? (cost(32) <= cost(8) ? 32 : 8) : (cost(16) <= cost(8) ? 16 : 8);
+    static constexpr int plain = cdiv((N / R1) * NB, NTH) + cdiv((N / R2) * NB, NTH);  // rounds of the barrier-separated passes
+    static constexpr bool ok = LPC_IP_WARPLOCAL && (32 % NB == 0) && (NTH % 32 == 0) && (M1 % 2 == 1) && (S2 % 2 == 1) &&
+                               cost(TS) <= plain;
+};
+// one PHASE (0 = the pass executed first, 1 = the second) of class c for lane (b, li) of a team with LPB idx-lanes;
+// host-callable: tests/csrc/test_fft_host.cpp walks the classes with exactly this function
+template <typename T, int DIR, bool DIF, int NB, int N, int R1, int R2, bool WIN>
+LPC_HD void fft_ip_outer2_phase(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int phase, int c, int b, int li, int LPB,
+                                int lo, int hi) {
+    constexpr int M1 = N / R1, S2 = M1 / R2, TWOFF2 = (R1 - 1) * (N / R1);
+    if ((phase == 0) == DIF) {  // the radix-R1 pass over the whole transform: butterflies n2 = c + S2*idx, idx < R2
+#pragma unroll 1
+        for (int idx = li; idx < R2; idx += LPB) fft_ip_bfly<T, R1, DIR, DIF, WIN>(sm + b, NB, N, c + S2 * idx, tw, lo, hi);
+    } else {                    // the radix-R2 pass inside the R1 blocks of M1: butterflies (blk = idx, n2' = c), idx < R1
+#pragma unroll 1
+        for (int idx = li; idx < R1; idx += LPB) fft_ip_bfly<T, R2, DIR, DIF>(sm + b, NB, M1, idx * S2 + c, tw + TWOFF2);
+    }
+}
+template <typename T, int DIR, bool DIF, int NB, int NTH, int N, int R1, int R2, bool WIN>
+__device__ __forceinline__ void cta_fft_ip_outer2(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, int lo, int hi) {
+    using W = IpWl<N, NB, NTH, R1, R2>;
+    constexpr int TS = W::TS, LPB = TS / NB, S2 = W::S2, NTEAM = (NTH / 32) * (32 / TS);
+    const int team = tid / TS, tl = tid % TS, b = tl % NB, li = tl / NB;
+#pragma unroll 1
+    for (int c = team; c < S2; c += NTEAM) {
+        fft_ip_outer2_phase<T, DIR, DIF, NB, N, R1, R2, WIN>(sm, tw, 0, c, b, li, LPB, lo, hi);
+        __syncwarp();
+        fft_ip_outer2_phase<T, DIR, DIF, NB, N, R1, R2, WIN>(sm, tw, 1, c, b, li, LPB, lo, hi);
+    }
+}
+template <typename T, int DIR, int NB, int NTH, int N, bool WIN, typename BAR, int R1, int R2, int... Rest>
+__device__ __forceinline__ void cta_fft_ip_dif_butlast_wl(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar, int lo, int hi) {
+    cta_fft_ip_outer2<T, DIR, true, NB, NTH, N, R1, R2, WIN>(sm, tw, tid, lo, hi);
+    constexpr int M2 = N / R1 / R2;
+    cta_fft_ip_dif_butlast<T, DIR, NB, NTH, N, M2, (R1 - 1) * (N / R1) + (R2 - 1) * M2, false, false, BAR, Rest...>(sm, tw, tid, bar);
+}
+template <typename T, int DIR, int NB, int NTH, int N, bool WIN, typename BAR, int R1, int R2, int... Rest>
+__device__ __forceinline__ void cta_fft_ip_dit_butinner_wl(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar, int lo, int hi) {
+    constexpr int M2 = N / R1 / R2;
+    cta_fft_ip_dit_butinner<T, DIR, NB, NTH, N, M2, (R1 - 1) * (N / R1) + (R2 - 1) * M2, false, BAR, Rest...>(sm, tw, tid, bar);
+    bar.sync();
+    cta_fft_ip_outer2<T, DIR, false, NB, NTH, N, R1, R2, WIN>(sm, tw, tid, lo, hi);
+}
+template <int N, int NB, int NTH, int... Rs> struct IpWlSel { static constexpr bool ok = false; };
+template <int N, int NB, int NTH, int R1, int R2, int R3, int... Rest> struct IpWlSel<N, NB, NTH, R1, R2, R3, Rest...> {
+    static constexpr bool ok = IpWl<N, NB, NTH, R1, R2>::ok;
+};
 
 template <typename SEQ> struct IpTraits;
 template <int N_, int... Rs> struct IpTraits<FftSeq<N_, Rs...>> {
@@ -404,13 +528,16 @@ template <int N_, int... Rs> struct IpTraits<FftSeq<N_, Rs...>> {
         return len;
     }
     static constexpr int tw_len = compute_tw_len();
-    template <typename T, int DIR, int NB, int NTH, typename BAR>
-    static __device__ __forceinline__ void dif_butlast(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
-        cta_fft_ip_dif_butlast<T, DIR, NB, NTH, N_, N_, 0, true, BAR, Rs...>(sm, tw, tid, bar);
+    // WIN: the transform's input is zero outside [lo, hi) and only that range of the inverse's output is wanted
+    template <typename T, int DIR, int NB, int NTH, typename BAR, bool WIN = false>
+    static __device__ __forceinline__ void dif_butlast(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar, int lo = 0, int hi = 0) {
+        if constexpr (IpWlSel<N_, NB, NTH, Rs...>::ok) cta_fft_ip_dif_butlast_wl<T, DIR, NB, NTH, N_, WIN, BAR, Rs...>(sm, tw, tid, bar, lo, hi);
+        else cta_fft_ip_dif_butlast<T, DIR, NB, NTH, N_, N_, 0, true, WIN, BAR, Rs...>(sm, tw, tid, bar, lo, hi);
     }
-    template <typename T, int DIR, int NB, int NTH, typename BAR>
-    static __device__ __forceinline__ void dit_butinner(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar) {
-        cta_fft_ip_dit_butinner<T, DIR, NB, NTH, N_, N_, 0, BAR, Rs...>(sm, tw, tid, bar);
+    template <typename T, int DIR, int NB, int NTH, typename BAR, bool WIN = false>
+    static __device__ __forceinline__ void dit_butinner(typename CxT<T>::type* sm, const typename CxT<T>::type* tw, int tid, BAR bar, int lo = 0, int hi = 0) {
+        if constexpr (IpWlSel<N_, NB, NTH, Rs...>::ok) cta_fft_ip_dit_butinner_wl<T, DIR, NB, NTH, N_, WIN, BAR, Rs...>(sm, tw, tid, bar, lo, hi);
+        else cta_fft_ip_dit_butinner<T, DIR, NB, NTH, N_, N_, 0, WIN, BAR, Rs...>(sm, tw, tid, bar, lo, hi);
     }
 };
 #endif  // __CUDACC__

@@ -71,14 +71,16 @@ constexpr int LPC_COLS_THREADS = 1024;  // variant 0; variant 1 (LPC_COLS_VARIAN
     X(320, 5, 16, 4) X(288, 9, 16, 2) X(270, 15, 9, 2) X(256, 16, 16) X(240, 15, 16) X(200, 5, 8, 5) X(128, 16, 8) X(125, 5, 5, 5) \
     X(75, 15, 5) X(64, 16, 4) X(54, 9, 6) \
     LPC_ROW_MENU_EXTRA(X)
-// (column sequences end in a small radix: that pass is fused with the spectral update in registers)
+// (column sequences end in a small radix: that pass is fused with the spectral update in registers; where the first radix
+//  can carry every factor of two of N -- 2160 = 16 * 135, 1200 = 16 * 75 ... -- it does: the two outer passes then run
+//  warp-locally without a group barrier between them, lpc_fft.cuh: IpWl)
 #define LPC_COL_MENU(X) \
     X(4096, 16, 16, 4, 4) X(3840, 16, 16, 5, 3) X(3200, 16, 10, 5, 4) \
-    X(3072, 16, 16, 4, 3) X(2880, 15, 16, 4, 3) X(2560, 16, 16, 10) X(2400, 15, 16, 10) X(2160, 15, 16, 9) X(2048, 16, 16, 8) \
-    X(1920, 15, 16, 8) X(1600, 16, 10, 10) X(1536, 12, 16, 8) X(1440, 15, 16, 6) X(1280, 16, 16, 5) X(1200, 15, 16, 5) \
+    X(3072, 16, 16, 4, 3) X(2880, 15, 16, 4, 3) X(2560, 16, 16, 10) X(2400, 15, 16, 10) X(2160, 16, 15, 9) X(2048, 16, 16, 8) \
+    X(1920, 15, 16, 8) X(1600, 16, 10, 10) X(1536, 12, 16, 8) X(1440, 15, 16, 6) X(1280, 16, 16, 5) X(1200, 16, 15, 5) \
     X(1080, 8, 15, 9) X(1024, 16, 16, 4) X(960, 15, 16, 4) X(800, 16, 10, 5) X(768, 16, 16, 3) X(720, 15, 16, 3) X(640, 16, 8, 5) \
-    X(600, 15, 8, 5) X(540, 4, 15, 9) X(512, 16, 8, 4) X(480, 15, 8, 4) X(405, 15, 9, 3) X(400, 16, 5, 5) X(384, 16, 8, 3) \
-    X(360, 15, 8, 3) X(320, 16, 5, 4) X(270, 15, 9, 2) X(256, 16, 16) X(240, 15, 16) X(200, 5, 8, 5) X(128, 16, 8) X(48, 16, 3) \
+    X(600, 8, 15, 5) X(540, 4, 15, 9) X(512, 16, 8, 4) X(480, 15, 8, 4) X(405, 15, 9, 3) X(400, 16, 5, 5) X(384, 16, 8, 3) \
+    X(360, 15, 8, 3) X(320, 16, 5, 4) X(270, 15, 9, 2) X(256, 16, 16) X(240, 15, 16) X(200, 8, 5, 5) X(128, 16, 8) X(48, 16, 3) \
     X(45, 15, 3) X(40, 5, 8) X(27, 9, 3) \
     LPC_COL_MENU_EXTRA(X)
 #endif

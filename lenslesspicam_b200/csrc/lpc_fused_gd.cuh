@@ -50,6 +50,124 @@ __device__ __forceinline__ int gdf_data_plane(int p, const GdFusedK& k) {
     return (b * k.Dd + (k.Dd == 1 ? 0 : dep)) * k.C + c;
 }
 
+// ---- the element-wise stage of the row kernels, on the RL pixels j + m*NSL that butterfly j of the last inverse pass holds
+//      (v[m].x: row ra, v[m].y: row rb); leaves the packed input of the forward transform in v
+template <typename T, int RL, int NSL, int MODE>
+__device__ __forceinline__ void gd_rows_elementwise(typename CxT<T>::type* v, int j, int sx, int w, bool has_b, int64_t ia, int64_t ib,
+                                                    int ra, int rb, const T* __restrict__ dpl, T* __restrict__ x, T* __restrict__ mom,
+                                                    T alpha, T scalar, int first) {
+    using C = typename CxT<T>::type;
+    if constexpr (MODE == LPC_GD_INIT || MODE == LPC_GD_RESID) {
+#pragma unroll
+        for (int m = 0; m < RL; ++m) {
+            const int col = j + m * NSL - sx;  // window column of padded pixel j + m*NSL
+            C z; z.x = T(0); z.y = T(0);       // everything outside the window is the zero padding
+            if (col >= 0 && col < w) {
+                if (MODE == LPC_GD_INIT) {
+                    z.x = x[ia + col];
+                    if (has_b) z.y = x[ib + col];
+                } else {
+                    z.x = v[m].x - dpl[(int64_t)ra * w + col];  // crop(Hx) - y   (gd.py:129)
+                    if (has_b) z.y = v[m].y - dpl[(int64_t)rb * w + col];
+                }
+            }
+            v[m] = z;
+        }
+    } else {
+        // update modes read AND write x / mom: a load that follows a store to the same array cannot be hoisted
+        // above it, so an element-by-element loop exposes one global-load latency per element (ncu, round 2: 48 %
+        // of the kernel's samples on the long scoreboard).  Elements are therefore handled in chunks: all loads of
+        // a chunk, then its arithmetic and stores -- gd_rows(update) 83 -> 66 us, FISTA-300 12.5 -> 13.4 recon/s.
+        // (The same batching of SHARED-memory reads ahead of stores in the gather / separation loops was measured
+        // slower -- B2 205 -> 226 us -- and is not used: there the interleaving feeds the LSU more evenly.)
+        constexpr int CH = 4;
+#pragma unroll
+        for (int m0 = 0; m0 < RL; m0 += CH) {
+            T xv[CH][2], pv[CH][2];
+#pragma unroll
+            for (int mm = 0; mm < CH; ++mm) {
+                const int m = m0 + mm;
+                xv[mm][0] = xv[mm][1] = pv[mm][0] = pv[mm][1] = T(0);
+                if (m < RL) {
+                    const int col = j + m * NSL - sx;
+                    if (col >= 0 && col < w) {
+                        xv[mm][0] = x[ia + col];
+                        if (has_b) xv[mm][1] = x[ib + col];
+                        if (MODE == LPC_GD_UPD_NESTEROV || (MODE == LPC_GD_UPD_FISTA && !first)) {
+                            pv[mm][0] = mom[ia + col];
+                            if (has_b) pv[mm][1] = mom[ib + col];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int mm = 0; mm < CH; ++mm) {
+                const int m = m0 + mm;
+                if (m < RL) {
+                    const int col = j + m * NSL - sx;
+                    C z; z.x = T(0); z.y = T(0);
+                    if (col >= 0 && col < w) {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            if (s == 1 && !has_b) break;
+                            const int64_t o = (s == 0 ? ia : ib) + col;
+                            const T gs = (s == 0) ? v[m].x : v[m].y;
+                            const T xo = xv[mm][s];
+                            T xn;
+                            if (MODE == LPC_GD_UPD_GD) {  // gd.py:132-134
+                                const T u = xo - alpha * gs;
+                                xn = u > T(0) ? u : T(0);
+                            } else if (MODE == LPC_GD_UPD_NESTEROV) {  // gd.py:183-188
+                                const T p_prev = pv[mm][s];
+                                const T p_new = scalar * p_prev - alpha * gs;
+                                mom[o] = p_new;
+                                const T u = xo + (-scalar * p_prev + (T(1) + scalar) * p_new);
+                                xn = u > T(0) ? u : T(0);
+                            } else {  // FISTA, gd.py:235-241
+                                const T zz = xo - alpha * gs;
+                                const T xk = zz > T(0) ? zz : T(0);
+                                const T prev = first ? zz : pv[mm][s];
+                                mom[o] = xk;
+                                xn = xk + scalar * (xk - prev);
+                            }
+                            x[o] = xn;
+                            if (s == 0) z.x = xn; else z.y = xn;
+                        }
+                    }
+                    v[m] = z;
+                }
+            }
+        }
+    }
+}
+
+// ---- separate the packed pair held in W (natural order) and store the two half-spectrum rows ra, ra+1 (no 1/2: folded
+//      into the filter); two lanes per 32-byte chunk, 16-byte stores
+template <typename T, int Wp, int PF>
+__device__ __forceinline__ void gd_rows_separate_store(const typename CxT<T>::type* W, typename CxT<T>::type* Tp, int64_t tile_stride,
+                                                       int ra, bool has_b, int tid) {
+    using C = typename CxT<T>::type;
+    constexpr int NTH = LPC_ROWS_THREADS, NC = LPC_GNC, Nh = Wp / 2 + 1, NTg = (Nh + NC - 1) / NC;
+    for (int g = tid; g < NTg * 2; g += NTH) {
+        const int t = g >> 1, hf = g & 1;
+        Vec16<T> oa, ob;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int kx = t * NC + hf * 2 + c;
+            oa.v[2 * c] = oa.v[2 * c + 1] = ob.v[2 * c] = ob.v[2 * c + 1] = T(0);
+            if (kx < Nh) {
+                const C zk = W[fft_pad(kx, PF)];
+                const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PF)];
+                oa.v[2 * c] = zk.x + zm.x; oa.v[2 * c + 1] = zk.y - zm.y;   // Z[k] + conj(Z[-k])
+                ob.v[2 * c] = zk.y + zm.y; ob.v[2 * c + 1] = zm.x - zk.x;   // (Z[k] - conj(Z[-k])) / i
+            }
+        }
+        C* da = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC + hf * 2;
+        st16(reinterpret_cast<T*>(da), oa);
+        if (has_b) st16(reinterpret_cast<T*>(da + NC), ob);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // rows: one CTA per pair of window rows (ra = 2*pair, rb = ra + 1) of one plane.   grid (ceil(h/2), planes)
 //   x, mom, data are planar UNPADDED [planes][h][w]; consts[3C + c] = alpha_c (gd.py:108-112)
@@ -127,88 +245,7 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
                 fft_bfly_load<T, RL>(W, 0, 1, PI, Wp, j, v[it]);
                 fft_bfly_compute<T, RL, +1>(v[it], twI + TR::tw_off_last, NSL, j);
             }
-            if constexpr (MODE == LPC_GD_INIT || MODE == LPC_GD_RESID) {
-#pragma unroll
-                for (int m = 0; m < RL; ++m) {
-                    const int col = j + m * NSL - sx;  // window column of padded pixel j + m*NSL
-                    C z; z.x = T(0); z.y = T(0);       // everything outside the window is the zero padding
-                    if (col >= 0 && col < w) {
-                        if (MODE == LPC_GD_INIT) {
-                            z.x = x[ia + col];
-                            if (has_b) z.y = x[ib + col];
-                        } else {
-                            z.x = v[it][m].x - dpl[(int64_t)ra * w + col];  // crop(Hx) - y   (gd.py:129)
-                            if (has_b) z.y = v[it][m].y - dpl[(int64_t)rb * w + col];
-                        }
-                    }
-                    v[it][m] = z;
-                }
-            } else {
-                // update modes read AND write x / mom: a load that follows a store to the same array cannot be hoisted
-                // above it, so an element-by-element loop exposes one global-load latency per element (ncu, round 2: 48 %
-                // of the kernel's samples on the long scoreboard).  Elements are therefore handled in chunks: all loads of
-                // a chunk, then its arithmetic and stores -- gd_rows(update) 83 -> 66 us, FISTA-300 12.5 -> 13.4 recon/s.
-                // (The same batching of SHARED-memory reads ahead of stores in the gather / separation loops was measured
-                // slower -- B2 205 -> 226 us -- and is not used: there the interleaving feeds the LSU more evenly.)
-                constexpr int CH = 4;
-#pragma unroll
-                for (int m0 = 0; m0 < RL; m0 += CH) {
-                    T xv[CH][2], pv[CH][2];
-#pragma unroll
-                    for (int mm = 0; mm < CH; ++mm) {
-                        const int m = m0 + mm;
-                        xv[mm][0] = xv[mm][1] = pv[mm][0] = pv[mm][1] = T(0);
-                        if (m < RL) {
-                            const int col = j + m * NSL - sx;
-                            if (col >= 0 && col < w) {
-                                xv[mm][0] = x[ia + col];
-                                if (has_b) xv[mm][1] = x[ib + col];
-                                if (MODE == LPC_GD_UPD_NESTEROV || (MODE == LPC_GD_UPD_FISTA && !first)) {
-                                    pv[mm][0] = mom[ia + col];
-                                    if (has_b) pv[mm][1] = mom[ib + col];
-                                }
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int mm = 0; mm < CH; ++mm) {
-                        const int m = m0 + mm;
-                        if (m < RL) {
-                            const int col = j + m * NSL - sx;
-                            C z; z.x = T(0); z.y = T(0);
-                            if (col >= 0 && col < w) {
-#pragma unroll
-                                for (int s = 0; s < 2; ++s) {
-                                    if (s == 1 && !has_b) break;
-                                    const int64_t o = (s == 0 ? ia : ib) + col;
-                                    const T gs = (s == 0) ? v[it][m].x : v[it][m].y;
-                                    const T xo = xv[mm][s];
-                                    T xn;
-                                    if (MODE == LPC_GD_UPD_GD) {  // gd.py:132-134
-                                        const T u = xo - alpha * gs;
-                                        xn = u > T(0) ? u : T(0);
-                                    } else if (MODE == LPC_GD_UPD_NESTEROV) {  // gd.py:183-188
-                                        const T p_prev = pv[mm][s];
-                                        const T p_new = scalar * p_prev - alpha * gs;
-                                        mom[o] = p_new;
-                                        const T u = xo + (-scalar * p_prev + (T(1) + scalar) * p_new);
-                                        xn = u > T(0) ? u : T(0);
-                                    } else {  // FISTA, gd.py:235-241
-                                        const T zz = xo - alpha * gs;
-                                        const T xk = zz > T(0) ? zz : T(0);
-                                        const T prev = first ? zz : pv[mm][s];
-                                        mom[o] = xk;
-                                        xn = xk + scalar * (xk - prev);
-                                    }
-                                    x[o] = xn;
-                                    if (s == 0) z.x = xn; else z.y = xn;
-                                }
-                            }
-                            v[it][m] = z;
-                        }
-                    }
-                }
-            }
+            gd_rows_elementwise<T, RL, NSL, MODE>(v[it], j, sx, w, has_b, ia, ib, ra, rb, dpl, x, mom, alpha, scalar, first);
             Dft<T, RL, -1>::run(v[it]);  // first pass of the reversed sequence: Ns = 1, no twiddles
         }
     }
@@ -221,26 +258,7 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
     __syncthreads();
     SeqTraits<REV>::template run_butfirst<T, -1, 1, NTH>(W, twF, tid);
 
-    // separate the packed pair and store the two half-spectrum rows (no 1/2: folded into the filter); two lanes per
-    // 32-byte chunk, 16-byte stores (see the gather)
-    for (int g = tid; g < NTg * 2; g += NTH) {
-        const int t = g >> 1, hf = g & 1;
-        Vec16<T> oa, ob;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int kx = t * NC + hf * 2 + c;
-            oa.v[2 * c] = oa.v[2 * c + 1] = ob.v[2 * c] = ob.v[2 * c + 1] = T(0);
-            if (kx < Nh) {
-                const C zk = W[fft_pad(kx, PF)];
-                const C zm = W[fft_pad(kx == 0 ? 0 : Wp - kx, PF)];
-                oa.v[2 * c] = zk.x + zm.x; oa.v[2 * c + 1] = zk.y - zm.y;   // Z[k] + conj(Z[-k])
-                ob.v[2 * c] = zk.y + zm.y; ob.v[2 * c + 1] = zm.x - zk.x;   // (Z[k] - conj(Z[-k])) / i
-            }
-        }
-        C* da = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC + hf * 2;
-        st16(reinterpret_cast<T*>(da), oa);
-        if (has_b) st16(reinterpret_cast<T*>(da + NC), ob);
-    }
+    gd_rows_separate_store<T, Wp, PF>(W, Tp, tile_stride, ra, has_b, tid);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -18,6 +18,10 @@
 #include "lpc_fused.cuh"
 #include "lpc_fused_tma.cuh"
 
+#ifndef LPC_B1_DIRECT
+#define LPC_B1_DIRECT 1
+#endif
+
 namespace lpc {
 
 __host__ __device__ constexpr int rows_tma_wlen(int n, int padsh) { return padsh >= 30 ? n + 1 : n + (n >> padsh) + 1; }  // = fft_padded_len
@@ -88,6 +92,26 @@ k_rows_ifft_tma(FusedK f, const __grid_constant__ CUtensorMap tmap, int n_items,
         const int p = f.plane0 + lin / Hp, row = lin - (lin / Hp) * Hp;
         mbar_wait(bar, phase);
         phase ^= 1;
+#if LPC_B1_DIRECT
+        // The first pass takes its input straight from the staging array: element i of Y = t*Vhat + i*HVhat is the 16-byte
+        // piece (Vhat[i], HVhat[i]) at byte i*16 for i <= Wp/2 and the conjugate-symmetric image of piece Wp-i above
+        // (two real rows per complex transform, see FusedK::pack) -- no expansion sweep, no extra barrier.
+        TR::template run_first_ld<T, +1, NTH>(W, tid, [&](int i) {
+            const bool lo = i < Nh;
+            const float4 c4 = S4[lo ? i : Wp - i];
+            const T vx = c4.x * pk.x, vy = c4.y * pk.x;
+            C y;
+            y.x = lo ? vx - c4.w : vx + c4.w;
+            y.y = lo ? vy + c4.z : c4.z - vy;
+            return y;
+        });
+        // (barrier passed: staging consumed, W holds the first pass's output)
+        if (tid == 0 && item + (int)gridDim.x < n_items) {
+            fence_proxy_async();  // order the generic-proxy reads of the staging array before the async-proxy writes
+            issue(item + (int)gridDim.x);
+        }
+        TR::template run_mid<T, +1, 1, NTH>(W, tw, tid);
+#else
         // staging -> transform buffer: column kx = the 16-byte piece (Vhat[kx], HVhat[kx]) at byte kx*16; expand the
         // Hermitian half (two real rows per complex transform: y = t*Vhat + i*HVhat, see FusedK::pack)
         for (int kx = tid; kx < Nh; kx += NTH) {
@@ -107,6 +131,7 @@ k_rows_ifft_tma(FusedK f, const __grid_constant__ CUtensorMap tmap, int n_items,
             issue(item + (int)gridDim.x);
         }
         TR::template run_butlast<T, +1, 1, NTH>(W, tw, tid);
+#endif
         T* Vout = VH + (int64_t)p * plane + (int64_t)row * Wp;
         T* HVout = Vout + (int64_t)f.n_planes * plane;
         for (int j = tid; j < NSL; j += NTH) {

@@ -85,6 +85,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
 // generic-proxy shared-memory writes -> visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifndef LPC_GD_WIN
+#define LPC_GD_WIN 1
+#endif
 constexpr int LPC_TMA_NBUF = 3;
 constexpr int LPC_TMA_MAXR = 16;
 
@@ -381,8 +384,10 @@ k_gd_cols_tma(GdFusedK f, int n_items, const typename CxT<T>::type* __restrict__
     const int grp = tid / NTHG, gtid = tid - grp * NTHG;
     const BarNamed<NTHG> bar{1 + grp};
     constexpr int NPAIR = NBL * NC;  // (butterfly, column) pairs of the middle stage
+#if !LPC_GD_WIN
     const int top16 = sy * (NC / 2);                  // 16-byte vectors above the window
     const int bot0 = (sy + h) * (NC / 2);             // first 16-byte vector below it
+#endif
     for (int e = grp; e < count; e += NG) {
         const int b = e % NBUF;
         C* sm = bufs + (size_t)b * n;
@@ -390,6 +395,13 @@ k_gd_cols_tma(GdFusedK f, int n_items, const typename CxT<T>::type* __restrict__
         const int p = f.plane0 + item / NTg, tile = item % NTg, q = p % f.DC;
         const C* Fq = Fm + ((int64_t)q * NTg + tile) * (int64_t)n;
         mbar_wait(full_bar(b), (uint32_t)((e / NBUF) & 1));
+#if LPC_GD_WIN
+        // Zero padding around the window: the bulk copy only writes the window rows; the others hold the output of the
+        // buffer's previous tile.  They are never read: the outermost forward pass takes every element outside the
+        // window as zero (and then defines the whole buffer, in place), the outermost inverse pass stores the window rows
+        // only -- no zero-fill sweep, no barrier for it, half the shared-memory loads / stores of those two passes.
+        IP::template dif_butlast<T, -1, NC, NTHG, BarNamed<NTHG>, true>(sm, tw_s, gtid, bar, sy, sy + h);
+#else
         // zero padding around the window: the bulk copy only writes the window rows, the others hold the output of
         // the buffer's previous tile.  Only now is the buffer ours -- its previous tile may belong to the OTHER
         // group, and the load completing is what proves that tile was computed and stored.
@@ -401,6 +413,7 @@ k_gd_cols_tma(GdFusedK f, int n_items, const typename CxT<T>::type* __restrict__
         }
         bar.sync();  // the zero rows of every thread are in place
         IP::template dif_butlast<T, -1, NC, NTHG>(sm, tw_s, gtid, bar);
+#endif
         int g = gtid;
         C Fv[RL];
         if (g < NPAIR) {
@@ -430,7 +443,11 @@ k_gd_cols_tma(GdFusedK f, int n_items, const typename CxT<T>::type* __restrict__
             for (int m = 0; m < RL; ++m) pp[m * NC] = v[m];
             g = gn;
         }
+#if LPC_GD_WIN
+        IP::template dit_butinner<T, +1, NC, NTHG, BarNamed<NTHG>, true>(sm, tw_s, gtid, bar, sy, sy + h);
+#else
         IP::template dit_butinner<T, +1, NC, NTHG>(sm, tw_s, gtid, bar);
+#endif
         fence_proxy_async();
         mbar_arrive(done_bar(b));
     }
