@@ -32,6 +32,13 @@
 namespace lpc {
 
 constexpr int LPC_GNC = 4;  // columns per tile of the G-layout
+// LPC_GD_HINTS = 1: the column kernel reads its filter table with an evict-first L2 policy.  The two tables (H and conj H,
+// 2 x 100 MB at 3x1080x1920) are streamed once per iteration each and used to flush the 125 MB of Tg / x / momentum / y
+// that ARE reused out of the 126 MB L2: FISTA-300 13.45 -> 13.92 recon/s (five A/B runs, profiles/README.md).  Further
+// hints on top (evict-first on the filter's L2 prefetch, on y, on the momentum; evict-last on Tg) changed nothing or cost.
+#ifndef LPC_GD_HINTS
+#define LPC_GD_HINTS 1
+#endif
 
 struct GdFusedK {
     int Hp, Wp, Nh, NTg;
