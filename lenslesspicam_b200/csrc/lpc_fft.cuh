@@ -490,11 +490,14 @@ __device__ __forceinline__ void cta_fft_ip_outer2(typename CxT<T>::type* sm, con
     using W = IpWl<N, NB, NTH, R1, R2>;
     constexpr int TS = W::TS, LPB = TS / NB, S2 = W::S2, NTEAM = (NTH / 32) * (32 / TS);
     const int team = tid / TS, tl = tid % TS, b = tl % NB, li = tl / NB;
+    // the trip count is uniform over the CTA, so every lane of a warp reaches the __syncwarp (teams smaller than a warp
+    // may run out of classes before their neighbours)
 #pragma unroll 1
-    for (int c = team; c < S2; c += NTEAM) {
-        fft_ip_outer2_phase<T, DIR, DIF, NB, N, R1, R2, WIN>(sm, tw, 0, c, b, li, LPB, lo, hi);
+    for (int c0 = 0; c0 < S2; c0 += NTEAM) {
+        const int c = c0 + team;
+        if (c < S2) fft_ip_outer2_phase<T, DIR, DIF, NB, N, R1, R2, WIN>(sm, tw, 0, c, b, li, LPB, lo, hi);
         __syncwarp();
-        fft_ip_outer2_phase<T, DIR, DIF, NB, N, R1, R2, WIN>(sm, tw, 1, c, b, li, LPB, lo, hi);
+        if (c < S2) fft_ip_outer2_phase<T, DIR, DIF, NB, N, R1, R2, WIN>(sm, tw, 1, c, b, li, LPB, lo, hi);
     }
 }
 template <typename T, int DIR, int NB, int NTH, int N, bool WIN, typename BAR, int R1, int R2, int... Rest>

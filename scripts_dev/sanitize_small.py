@@ -27,7 +27,7 @@ def blur(x, nl):
 
 
 def main():
-    for (h, w, C) in ((24, 32, 3), (23, 38, 3), (135, 240, 1), (64, 100, 1)):
+    for (h, w, C) in ((24, 32, 3), (23, 38, 3), (135, 240, 1), (64, 100, 1), (100, 120, 1)):  # 100 -> padded 200 = 8.5.5: warp-local column passes
         psf, data = problem(h, w, C)
         for cls in (L.ADMM, L.FISTA, L.GradientDescent, L.NesterovGradientDescent):
             rec = cls(psf)

@@ -6,6 +6,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "lpc_fft_plan.h"
@@ -167,6 +168,61 @@ template <typename T> static double test_ip(int N, int nbatch) {
     return fmax(err / mx, err2);
 }
 
+// ---- the warp-local pair of outermost passes (fft_ip_outer2_phase): classes walked ONE AFTER THE OTHER, each through its
+//      two phases -- correct only if a class really depends on nothing outside itself.  WIN: zero padding outside [lo, hi):
+//      the forward side must not read outside the window (garbage is planted there), the inverse side only has to
+//      deliver the window.
+template <typename T, int N, int R1, int R2, int R3, bool WIN> static double test_ip_outer2() {
+    using C = typename CxT<T>::type;
+    constexpr int NB = 4, M1 = N / R1, S2 = M1 / R2, LPB = 8;
+    static_assert(R1 * R2 * R3 == N, "three-pass sequence");
+    const int radix[3] = {R1, R2, R3};
+    std::vector<C> tw;
+    if (!fill_fft_ip_twiddles(N, radix, 3, &tw)) { printf("no ip twiddles for %d\n", N); exit(2); }
+    const int lo = WIN ? N / 4 + 1 : 0, hi = WIN ? N / 4 + N / 2 : N;
+    std::vector<C> sm((size_t)N * NB);
+    std::vector<std::vector<std::complex<long double>>> x(NB, std::vector<std::complex<long double>>(N));
+    for (int b = 0; b < NB; ++b)
+        for (int i = 0; i < N; ++i) {
+            C c; c.x = (T)(rand() / (double)RAND_MAX - 0.5); c.y = (T)(rand() / (double)RAND_MAX - 0.5);
+            sm[(size_t)i * NB + b] = c;
+            x[b][i] = (i >= lo && i < hi) ? std::complex<long double>(c.x, c.y) : std::complex<long double>(0, 0);
+        }
+    const C* tw3 = tw.data() + (R1 - 1) * (N / R1) + (R2 - 1) * S2;
+    auto outer = [&](auto dif) {
+        constexpr bool DIF = decltype(dif)::value;
+        for (int c = 0; c < S2; ++c)
+            for (int phase = 0; phase < 2; ++phase)
+                for (int b = 0; b < NB; ++b)
+                    for (int li = 0; li < LPB; ++li)
+                        fft_ip_outer2_phase<T, DIF ? -1 : +1, DIF, NB, N, R1, R2, WIN>(sm.data(), tw.data(), phase, c, b, li, LPB, lo, hi);
+    };
+    outer(std::true_type{});
+    emu_ip_pass<T, R3, -1, true>(sm, tw3, N, R3, NB);
+    double err = 0, mx = 0;
+    for (int b = 0; b < NB; ++b) {
+        std::vector<std::complex<long double>> X;
+        naive<T, -1>(x[b], X);
+        for (int p = 0; p < N; ++p) {
+            const int k = fft_ip_freq_of_pos(N, radix, 3, p);
+            C c = sm[(size_t)p * NB + b];
+            err = fmax(err, (double)std::abs(std::complex<long double>(c.x, c.y) - X[k]));
+            mx = fmax(mx, (double)std::abs(X[k]));
+        }
+    }
+    emu_ip_pass<T, R3, +1, false>(sm, tw3, N, R3, NB);
+    outer(std::false_type{});
+    double err2 = 0;
+    for (int b = 0; b < NB; ++b)
+        for (int i = lo; i < hi; ++i) {
+            C c = sm[(size_t)i * NB + b];
+            err2 = fmax(err2, (double)std::abs(std::complex<long double>(c.x / N, c.y / N) - x[b][i]));
+        }
+    printf("N=%5d warp-local outer passes (%d,%d | %d) %s  fwd rel err %.2e  round-trip err %.2e\n", N, R1, R2, R3,
+           WIN ? "windowed" : "full    ", err / mx, err2);
+    return fmax(err / mx, err2);
+}
+
 int main() {
     int bad = 0;
     double e;
@@ -187,6 +243,13 @@ int main() {
         if (test_ip<double>(N, 1) > 1e-13) bad++;
         if (test_ip<float>(N, 4) > 2e-6) bad++;
     }
+#define TW(N, A, B, C3) \
+    if (test_ip_outer2<double, N, A, B, C3, false>() > 1e-13) bad++; \
+    if (test_ip_outer2<float, N, A, B, C3, false>() > 2e-6) bad++;   \
+    if (test_ip_outer2<double, N, A, B, C3, true>() > 1e-13) bad++;  \
+    if (test_ip_outer2<float, N, A, B, C3, true>() > 2e-6) bad++;
+    TW(2160, 16, 15, 9) TW(1080, 8, 15, 9) TW(405, 15, 9, 3) TW(400, 16, 5, 5) TW(2160, 15, 16, 9)
+#undef TW
     printf(bad ? "FAILED (%d)\n" : "ALL OK\n", bad);
     return bad ? 1 : 0;
 }
