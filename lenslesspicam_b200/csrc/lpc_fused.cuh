@@ -108,6 +108,25 @@ struct FusedK {
 __device__ __forceinline__ int lpc_dir_x(const FusedK& f, int n) { return f.rev ? n - 1 - (int)blockIdx.x : (int)blockIdx.x; }
 __device__ __forceinline__ int lpc_dir_y(const FusedK& f) { return f.plane0 + (f.rev ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y); }
 
+// L1 allocation of B2's single-use streams (LPC_B2_NA: bit 0 the stores, bit 1 the single-use loads): see lpc_util.cuh
+#ifndef LPC_B2_NA
+#define LPC_B2_NA 3
+#endif
+#if LPC_B2_NA & 1
+#define LPC_B2_ST st16_hint_na
+#else
+#define LPC_B2_ST st16_hint
+#endif
+#if LPC_B2_NA & 2
+#define LPC_B2_LDNC ld16_nc_hint_na
+#define LPC_B2_LD ld16_hint_na
+#else
+#define LPC_B2_LDNC ld16_nc_hint
+#define LPC_B2_LD ld16_hint
+#endif
+#ifndef LPC_B2_PF_BULK
+#define LPC_B2_PF_BULK 1
+#endif
 constexpr int LPC_ROWS_RY = 4;  // rows a B2 CTA processes back to back
 
 // ---- B helper: forward FFT of the row held in W (z = a + i*xi'), separate the two real spectra
@@ -134,7 +153,7 @@ __device__ __forceinline__ void rows_fft_store(typename CxT<T>::type* W, const t
                 o.v[2] = (zk.y + zm.y) * sep_scale_im;  // Xi = (Z[k] - conj(Z[-k])) / i
                 o.v[3] = (zm.x - zk.x) * sep_scale_im;
             }
-            st16_hint(reinterpret_cast<T*>(Tdst + (int64_t)(kx / NCT) * tile_stride + (int64_t)row * (2 * NCT) + (kx % NCT) * 2), o,
+            LPC_B2_ST(reinterpret_cast<T*>(Tdst + (int64_t)(kx / NCT) * tile_stride + (int64_t)row * (2 * NCT) + (kx % NCT) * 2), o,
                       LPC_L2_EVICT_LAST);  // the column kernel reads it next
         }
     } else {
@@ -309,16 +328,16 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
                     const unsigned long long pol_up = f.rev ? LPC_L2_EVICT_NORMAL : LPC_L2_HALO;
                     const unsigned long long pol_dn = f.rev ? LPC_L2_HALO : LPC_L2_EVICT_NORMAL;
                     const Vec16<T> vc = ld16_nc(V + ro + j), vp = ld16_nc_hint(V + ru + j, pol_up), vn = ld16_nc_hint(V + rd + j, pol_dn);
-                    const Vec16<T> hv = ld16_nc_hint(HV + ro + j, LPC_L2_EVICT_FIRST);
+                    const Vec16<T> hv = LPC_B2_LDNC(HV + ro + j, LPC_L2_EVICT_FIRST);
                     const Vec16<T> e0 = ld16_nc_hint(eta0 + ro + j, pol_up), e0d = ld16_nc_hint(eta0 + rd + j, pol_dn);
-                    const Vec16<T> e1 = ld16_nc_hint(eta1 + ro + j, LPC_L2_STREAM);
-                    const Vec16<T> xih = ld16_hint(xip + ro + j, LPC_L2_STREAM), rhoh = ld16_hint(rhop + ro + j, LPC_L2_STREAM);
+                    const Vec16<T> e1 = ld16_nc_hint(eta1 + ro + j, LPC_L2_STREAM);  // (its neighbour column e1r re-reads the line)
+                    const Vec16<T> xih = LPC_B2_LD(xip + ro + j, LPC_L2_STREAM), rhoh = LPC_B2_LD(rhop + ro + j, LPC_L2_STREAM);
                     const T e1r = __ldg(eta1 + ro + jr);
                     const T vl = __ldg(V + ro + jl), vr = __ldg(V + ro + jr);
                     Vec16<T> y;
                     y.v[0] = y.v[1] = y.v[2] = y.v[3] = T(0);
                     if (row_in && j >= k.dcol0 && j < k.dcol0 + k.dpitch)
-                        y = ld16_nc_hint(dp + (int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0), LPC_L2_STREAM);
+                        y = LPC_B2_LDNC(dp + (int64_t)(i - k.sy) * k.dpitch + (j - k.dcol0), LPC_L2_STREAM);
                     Vec16<T> t1, e1new, e0new, xin, rhon;
                     T t0[4], t0d[4], dummy, av[4];
 #pragma unroll
@@ -351,10 +370,10 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
 #pragma unroll
                         for (int e = 0; e < 4; ++e) { C z; z.x = av[e]; z.y = xin.v[e] * f.pack_s; W[fft_pad(j + e, PADSH)] = z; }
                     }
-                    st16_hint(xip + ro + j, xin, LPC_L2_STREAM);  // the duals are not touched again for a whole iteration
-                    st16_hint(rhop + ro + j, rhon, LPC_L2_STREAM);
-                    st16_hint(eta0_o + ro + j, e0new, LPC_L2_STREAM);
-                    st16_hint(eta1_o + ro + j, e1new, LPC_L2_STREAM);
+                    LPC_B2_ST(xip + ro + j, xin, LPC_L2_STREAM);  // the duals are not touched again for a whole iteration
+                    LPC_B2_ST(rhop + ro + j, rhon, LPC_L2_STREAM);
+                    LPC_B2_ST(eta0_o + ro + j, e0new, LPC_L2_STREAM);
+                    LPC_B2_ST(eta1_o + ro + j, e1new, LPC_L2_STREAM);
                 }
             }
         } else {
@@ -392,11 +411,24 @@ k_rows_spatial_fft(FusedK f, AdmmK<T> k, const typename CxT<T>::type* __restrict
             if (lin >= 0 && lin < (int64_t)gridDim.y * Hp) {
                 const int pp = f.plane0 + (int)(lin / Hp), ii = (int)(lin % Hp);
                 const int64_t o = (int64_t)pp * plane + (int64_t)ii * Wp;
-                const T* rows6[6] = {VH + o, VH + (int64_t)f.n_planes * plane + o, xi + o, rho + o, eta_in + o, eta_in + eta1_off + o};
-                constexpr int LPR = (Wp * (int)sizeof(T) + 127) / 128;  // 128-byte lines per row
+#if LPC_B2_PF_BULK
+                if constexpr ((Wp * (int)sizeof(T)) % 16 == 0) {
+                    // one bulk prefetch per stream (cp.async.bulk.prefetch.L2, issued by six lanes) instead of one
+                    // prefetch instruction per 128-byte line: the per-line form cost the LSU data pipe ~720 wavefronts per row
+                    if (tid < 6) {
+                        const T* ptr = tid == 0 ? VH + o : tid == 1 ? VH + (int64_t)f.n_planes * plane + o : tid == 2 ? xi + o
+                                     : tid == 3 ? rho + o : tid == 4 ? eta_in + o : eta_in + eta1_off + o;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(Wp * (int)sizeof(T)) : "memory");
+                    }
+                } else
+#endif
+                {
+                    const T* rows6[6] = {VH + o, VH + (int64_t)f.n_planes * plane + o, xi + o, rho + o, eta_in + o, eta_in + eta1_off + o};
+                    constexpr int LPR = (Wp * (int)sizeof(T) + 127) / 128;  // 128-byte lines per row
 #pragma unroll
-                for (int a = 0; a < 6; ++a)
-                    for (int l = tid; l < LPR; l += NTH) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rows6[a]) + (size_t)l * 128));
+                    for (int a = 0; a < 6; ++a)
+                        for (int l = tid; l < LPR; l += NTH) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(rows6[a]) + (size_t)l * 128));
+                }
             }
         }
         rows_fft_store<T, SEQ>(W, tw, ToutP, tile_stride, i, NT, T(1), tid, f.inv_pack_s);

@@ -39,6 +39,11 @@ constexpr int LPC_GNC = 4;  // columns per tile of the G-layout
 #ifndef LPC_GD_HINTS
 #define LPC_GD_HINTS 1
 #endif
+// LPC_GD_NA: the row kernel's single-use streams bypass L1 allocation (bit 0: stores of x / momentum / Tg -- measured slower, more spills in the update variants --, bit 1: loads of
+// Tg / x / momentum / y), so that its two twiddle tables stay L1-resident (lpc_util.cuh)
+#ifndef LPC_GD_NA
+#define LPC_GD_NA 2
+#endif
 
 struct GdFusedK {
     int Hp, Wp, Nh, NTg;
@@ -74,8 +79,13 @@ __device__ __forceinline__ void gd_rows_elementwise(typename CxT<T>::type* v, in
                     z.x = x[ia + col];
                     if (has_b) z.y = x[ib + col];
                 } else {
-                    z.x = v[m].x - dpl[(int64_t)ra * w + col];  // crop(Hx) - y   (gd.py:129)
-                    if (has_b) z.y = v[m].y - dpl[(int64_t)rb * w + col];
+                    if constexpr ((LPC_GD_NA & 2) != 0 && sizeof(T) == 4) {
+                        z.x = v[m].x - ld4_nc_na(dpl + (int64_t)ra * w + col);  // crop(Hx) - y   (gd.py:129)
+                        if (has_b) z.y = v[m].y - ld4_nc_na(dpl + (int64_t)rb * w + col);
+                    } else {
+                        z.x = v[m].x - dpl[(int64_t)ra * w + col];
+                        if (has_b) z.y = v[m].y - dpl[(int64_t)rb * w + col];
+                    }
                 }
             }
             v[m] = z;
@@ -98,11 +108,20 @@ __device__ __forceinline__ void gd_rows_elementwise(typename CxT<T>::type* v, in
                 if (m < RL) {
                     const int col = j + m * NSL - sx;
                     if (col >= 0 && col < w) {
-                        xv[mm][0] = x[ia + col];
-                        if (has_b) xv[mm][1] = x[ib + col];
-                        if (MODE == LPC_GD_UPD_NESTEROV || (MODE == LPC_GD_UPD_FISTA && !first)) {
-                            pv[mm][0] = mom[ia + col];
-                            if (has_b) pv[mm][1] = mom[ib + col];
+                        if constexpr ((LPC_GD_NA & 2) != 0 && sizeof(T) == 4) {
+                            xv[mm][0] = ld4_na(x + ia + col);
+                            if (has_b) xv[mm][1] = ld4_na(x + ib + col);
+                            if (MODE == LPC_GD_UPD_NESTEROV || (MODE == LPC_GD_UPD_FISTA && !first)) {
+                                pv[mm][0] = ld4_na(mom + ia + col);
+                                if (has_b) pv[mm][1] = ld4_na(mom + ib + col);
+                            }
+                        } else {
+                            xv[mm][0] = x[ia + col];
+                            if (has_b) xv[mm][1] = x[ib + col];
+                            if (MODE == LPC_GD_UPD_NESTEROV || (MODE == LPC_GD_UPD_FISTA && !first)) {
+                                pv[mm][0] = mom[ia + col];
+                                if (has_b) pv[mm][1] = mom[ib + col];
+                            }
                         }
                     }
                 }
@@ -127,17 +146,17 @@ __device__ __forceinline__ void gd_rows_elementwise(typename CxT<T>::type* v, in
                             } else if (MODE == LPC_GD_UPD_NESTEROV) {  // gd.py:183-188
                                 const T p_prev = pv[mm][s];
                                 const T p_new = scalar * p_prev - alpha * gs;
-                                mom[o] = p_new;
+                                if constexpr ((LPC_GD_NA & 1) != 0 && sizeof(T) == 4) st4_na(mom + o, p_new); else mom[o] = p_new;
                                 const T u = xo + (-scalar * p_prev + (T(1) + scalar) * p_new);
                                 xn = u > T(0) ? u : T(0);
                             } else {  // FISTA, gd.py:235-241
                                 const T zz = xo - alpha * gs;
                                 const T xk = zz > T(0) ? zz : T(0);
                                 const T prev = first ? zz : pv[mm][s];
-                                mom[o] = xk;
+                                if constexpr ((LPC_GD_NA & 1) != 0 && sizeof(T) == 4) st4_na(mom + o, xk); else mom[o] = xk;
                                 xn = xk + scalar * (xk - prev);
                             }
-                            x[o] = xn;
+                            if constexpr ((LPC_GD_NA & 1) != 0 && sizeof(T) == 4) st4_na(x + o, xn); else x[o] = xn;
                             if (s == 0) z.x = xn; else z.y = xn;
                         }
                     }
@@ -170,8 +189,13 @@ __device__ __forceinline__ void gd_rows_separate_store(const typename CxT<T>::ty
             }
         }
         C* da = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC + hf * 2;
-        st16(reinterpret_cast<T*>(da), oa);
-        if (has_b) st16(reinterpret_cast<T*>(da + NC), ob);
+        if constexpr ((LPC_GD_NA & 1) != 0 && sizeof(T) == 4) {
+            st16_na(reinterpret_cast<T*>(da), oa);
+            if (has_b) st16_na(reinterpret_cast<T*>(da + NC), ob);
+        } else {
+            st16(reinterpret_cast<T*>(da), oa);
+            if (has_b) st16(reinterpret_cast<T*>(da + NC), ob);
+        }
     }
 }
 
@@ -215,10 +239,10 @@ k_gd_rows(GdFusedK f, const typename CxT<T>::type* __restrict__ twI, const typen
         for (int g = tid; g < NTg * 2; g += NTH) {
             const int t = g >> 1, hf = g & 1;
             const C* sa = Tp + (int64_t)t * tile_stride + (int64_t)ra * NC + hf * 2;
-            const Vec16<T> va = ld16_nc(reinterpret_cast<const T*>(sa));
+            const Vec16<T> va = (LPC_GD_NA & 2) ? ld16_nc_na(reinterpret_cast<const T*>(sa)) : ld16_nc(reinterpret_cast<const T*>(sa));
             Vec16<T> vb;
             vb.v[0] = vb.v[1] = vb.v[2] = vb.v[3] = T(0);
-            if (has_b) vb = ld16_nc(reinterpret_cast<const T*>(sa + NC));
+            if (has_b) vb = (LPC_GD_NA & 2) ? ld16_nc_na(reinterpret_cast<const T*>(sa + NC)) : ld16_nc(reinterpret_cast<const T*>(sa + NC));
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int kx = t * NC + hf * 2 + c;

@@ -21,6 +21,10 @@
 #ifndef LPC_B1_DIRECT
 #define LPC_B1_DIRECT 1
 #endif
+// V / HV are written once and read by the next kernel: no L1 allocation, the twiddle tables stay resident (lpc_util.cuh)
+#ifndef LPC_B1_ST
+#define LPC_B1_ST st4_hint_na
+#endif
 
 namespace lpc {
 
@@ -140,8 +144,8 @@ k_rows_ifft_tma(FusedK f, const __grid_constant__ CUtensorMap tmap, int n_items,
             fft_bfly_compute<T, RL, +1>(v, tw + TR::tw_off_last, NSL, j);
 #pragma unroll
             for (int m = 0; m < RL; ++m) {  // B2 reads them next
-                st4_hint(Vout + j + m * NSL, v[m].x * pk.y, LPC_L2_EVICT_LAST);
-                st4_hint(HVout + j + m * NSL, v[m].y, LPC_L2_EVICT_LAST);
+                LPC_B1_ST(Vout + j + m * NSL, v[m].x * pk.y, LPC_L2_EVICT_LAST);
+                LPC_B1_ST(HVout + j + m * NSL, v[m].y, LPC_L2_EVICT_LAST);
             }
         }
         __syncthreads();  // W is rewritten by the next item
