@@ -39,6 +39,9 @@ template <> struct CxT<double> { using type = double2; };
 #ifndef LPC_PACKED2
 #define LPC_PACKED2 0
 #endif
+#ifndef LPC_TW_PRODUCTS
+#define LPC_TW_PRODUCTS 1
+#endif
 template <typename C> LPC_HD C cx_add(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> LPC_HD C cx_sub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && LPC_PACKED2
@@ -159,17 +162,50 @@ LPC_HD void fft_bfly_compute(typename CxT<T>::type* v, const typename CxT<T>::ty
     using C = typename CxT<T>::type;
     if (Ns > 1) {
         const int k = j % Ns;
+#if LPC_TW_PRODUCTS
+        if constexpr (R >= 6) {
+            // Only the twiddles w^1, w^2, w^4, w^8 of the butterfly come from the table; the others are products of those
+            // (at most three deep: 7 = (1*2)*4, 15 = 7*8).  The row kernels are bound by the LSU data pipe, where the 15
+            // table loads per butterfly and pass were a fifth of the wavefronts, while their FMA pipe is a third busy
+            // (timing experiment without any twiddle load: B1 83 -> 74 us, GD rows 62 / 65 -> 57 / 59 us).  Accuracy: the host
+            // harness (tests/csrc/test_fft_host.cpp) measures the transforms against a long-double DFT with this scheme.
+            C w[R];
 #pragma unroll
-        for (int m = 1; m < R; ++m) {
-#if defined(__CUDA_ARCH__) && defined(LPC_EXP_NO_TW)
-            C w; w.x = (T)1 - (T)1e-9 * (T)k; w.y = (T)1e-9 * (T)m;   // timing experiment only: no table loads
-#elif defined(__CUDA_ARCH__)
-            C w = __ldg(tw + (m - 1) * Ns + k);
+            for (int m = 1; m < R; m *= 2) {
+#if defined(__CUDA_ARCH__)
+                w[m] = __ldg(tw + (m - 1) * Ns + k);
 #else
-            C w = tw[(m - 1) * Ns + k];
+                w[m] = tw[(m - 1) * Ns + k];
 #endif
-            if (DIR > 0) w.y = -w.y;
-            v[m] = cx_mul(v[m], w);
+                if (DIR > 0) w[m].y = -w[m].y;
+            }
+#pragma unroll
+            for (int m = 3; m < R && m < 8; ++m) {
+                const int hb = m >= 4 ? 4 : 2;  // highest power of two in m
+                if (m != hb) w[m] = cx_mul(w[m - hb], w[hb]);
+            }
+#pragma unroll
+            for (int m = 1; m < R && m < 8; ++m) v[m] = cx_mul(v[m], w[m]);
+            if constexpr (R > 8) {
+                v[8] = cx_mul(v[8], w[8]);
+#pragma unroll
+                for (int m = 9; m < R; ++m) v[m] = cx_mul(v[m], cx_mul(w[m - 8], w[8]));  // (w^9 .. w^15 are never all live)
+            }
+        } else
+#endif
+        {
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+#if defined(__CUDA_ARCH__) && defined(LPC_EXP_NO_TW)
+                C w; w.x = (T)1 - (T)1e-9 * (T)k; w.y = (T)1e-9 * (T)m;   // timing experiment only: no table loads
+#elif defined(__CUDA_ARCH__)
+                C w = __ldg(tw + (m - 1) * Ns + k);
+#else
+                C w = tw[(m - 1) * Ns + k];
+#endif
+                if (DIR > 0) w.y = -w.y;
+                v[m] = cx_mul(v[m], w);
+            }
         }
     }
     Dft<T, R, DIR>::run(v);
